@@ -1,0 +1,162 @@
+/*
+ * warpcore.h -- C ABI of the B200-native execution core that replaces WarpDB's
+ * jit.cpp / operator half of warpdb.cpp / optimizer.cpp / multi_gpu_utils.cpp.
+ *
+ * The reference has no FFI layer; its seam is the five free functions of
+ * include/jit.hpp:7-27 and include/multi_gpu_utils.hpp:10-12 (callers:
+ * src/warpdb.cpp:247,365,371,450,454,541,585; src/optimizer.cpp:51; src/main.cu:18,44,331).
+ * Each entry point below names the reference interface it replaces.  The C++ shims with the
+ * reference's exact signatures live in warpdb_b200/csrc/host/ (jit.hpp, multi_gpu_utils.hpp,
+ * optimizer.hpp, warpdb.hpp) and INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; wdb_last_error() returns the
+ *    message (thread local).  NVRTC failures use the reference's text "Kernel compilation
+ *    failed." (src/jit.cpp:128) with the compile log on stderr (src/jit.cpp:123-125).
+ *  - expressions are the CUDA-C strings produced by ASTNode::to_cuda_expr()
+ *    (include/expression.hpp:29-79): `col[idx]` names a column, literals carry an `f` suffix.
+ *    They are compiled with NVRTC for sm_100a with the reference's flags (arch only, so
+ *    --fmad=true, IEEE div/sqrt: src/jit.cpp:114-117), after the UDF source (custom.cu).
+ *  - device pointers are plain CUDA pointers of the primary context of `device`; `stream` is a
+ *    cudaStream_t (NULL = legacy default stream).  Calls are asynchronous on `stream` unless a
+ *    host output pointer (h_*) is passed, in which case they synchronise that stream.
+ *  - row counts are 64-bit (the reference's `int N` overflows at 4e9/8e9 rows: SURVEY F8).
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef WARPCORE_H
+#define WARPCORE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WDB_ABI_VERSION 1
+
+/* DataType, in the enum order of include/csv_loader.hpp:13 */
+enum { WDB_INT32 = 0, WDB_INT64 = 1, WDB_FLOAT32 = 2, WDB_FLOAT64 = 3, WDB_STRING = 4 };
+/* AggregationType, in the enum order of include/expression.hpp:86 */
+enum { WDB_SUM = 0, WDB_AVG = 1, WDB_COUNT = 2, WDB_MIN = 3, WDB_MAX = 4 };
+/* output modes of wdb_project_filter */
+enum {
+  WDB_DENSE = 0,      /* reference semantics (src/jit.cpp:55-61): rows failing cond leave out[i] untouched */
+  WDB_COMPACT = 1,    /* stable stream compaction: surviving values packed in row order */
+  WDB_DENSE_ZERO = 2  /* dense, rows failing cond write 0.0f (what WarpDB::query returns: SURVEY App. D) */
+};
+/* group output order */
+enum { WDB_ORDER_FIRST = 0 /* src/jit.cpp:196-213 */, WDB_ORDER_KEY_ASC = 1 /* std::map, src/warpdb.cpp:425 */, WDB_ORDER_KEY_DESC = 2 };
+
+/* ColumnDesc of include/csv_loader.hpp:15-20 (length widened to 64 bit) */
+typedef struct wdb_col {
+  const char *name;
+  int dtype;
+  const void *dptr;
+  int64_t len;
+} wdb_col_t;
+
+/* ---- library / device state ------------------------------------------------------------ */
+int wdb_abi_version(void);
+const char *wdb_last_error(void);
+/* Retain the primary context of `device`, check it is an sm_100-family part and create the
+ * per-device kernel cache.  Idempotent.  Replaces cuInit/cuCtxCreate of src/jit.cpp:104,153-155. */
+int wdb_init(int device);
+int wdb_shutdown(void);
+int wdb_device_count(int *out);
+/* Source prepended to every generated kernel: the contents of ./custom.cu (src/jit.cpp:65-73).
+ * NULL or "" clears it.  The C++ shim re-reads the file per call like the reference does. */
+int wdb_set_udf_source(const char *cuda_src);
+/* Tuning knobs ("project.variant", "project.block", "project.unroll", ...); see DESIGN.md. */
+int wdb_set_option(const char *key, int64_t value);
+int wdb_get_option(const char *key, int64_t *value);
+/* Statistics of the kernel cache and of the last call on this thread. */
+typedef struct wdb_stats {
+  int64_t kernels_compiled;   /* NVRTC compilations so far */
+  int64_t cache_hits;
+  int64_t launches;           /* kernel launches issued by this library so far */
+  double last_compile_ms;     /* NVRTC + module load time of the last miss */
+} wdb_stats_t;
+int wdb_get_stats(wdb_stats_t *out);
+
+/* ---- fused filter + project:  jit_compile_and_launch (include/jit.hpp:7-10, src/jit.cpp:48-174)
+ * cols: all columns of the table (only the ones the strings mention are read).
+ * expr: value expression; cond: "" or NULL for none.
+ * d_out: float[n] (DENSE*) or float[>= survivors] (COMPACT; n is always enough).
+ * d_count: optional device int64 receiving the survivor count (COMPACT) or n (dense modes).
+ * h_count: optional host int64; if non-NULL the call synchronises `stream`. */
+int wdb_project_filter(int device, void *stream, const wdb_col_t *cols, int ncols, const char *expr,
+                       const char *cond, float *d_out, int64_t n, int mode, int64_t *d_count,
+                       int64_t *h_count);
+
+/* ---- hash GROUP BY:  jit_group_sum (include/jit.hpp:15-18, src/jit.cpp:179-246) and the
+ * std::map aggregation of src/warpdb.cpp:373-437.  key = (int)key_expr, fp64 accumulators.
+ * An aggregation table is an opaque per-device object so that chunks (query_multi_gpu_csv) and
+ * partial aggregates of other GPUs can be folded into it. */
+typedef struct wdb_agg wdb_agg_t;
+int wdb_agg_create(int device, int64_t expected_groups, wdb_agg_t **out);
+int wdb_agg_destroy(wdb_agg_t *t);
+int wdb_agg_reset(wdb_agg_t *t, void *stream);
+/* fold n rows into the table (cond "" = none).  row_base is the global index of row 0 (first-appearance order). */
+int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols, const char *val_expr,
+                    const char *key_expr, const char *cond, int64_t n, int64_t row_base);
+/* fold m partial groups (as exported with the raw arrays below) into the table */
+int wdb_agg_merge(wdb_agg_t *t, void *stream, const int32_t *d_keys, const double *d_sums,
+                  const int64_t *d_counts, const double *d_mins, const double *d_maxs,
+                  const int64_t *d_first, int64_t m);
+/* number of groups (synchronises) */
+int wdb_agg_size(wdb_agg_t *t, void *stream, int64_t *h_groups);
+/* export groups in `order`; any output pointer may be NULL.  d_vals holds float(agg result)
+ * per src/warpdb.cpp:429-435.  cap = capacity of the output arrays.  Synchronises. */
+int wdb_agg_export(wdb_agg_t *t, void *stream, int agg, int order, int32_t *d_keys, float *d_vals,
+                   double *d_sums, int64_t *d_counts, double *d_mins, double *d_maxs, int64_t *d_first,
+                   int64_t cap, int64_t *h_groups);
+/* one-shot convenience: create + consume + export + destroy */
+int wdb_group_agg(int device, void *stream, const wdb_col_t *cols, int ncols, const char *val_expr,
+                  const char *key_expr, const char *cond, int agg, int order, int64_t n,
+                  int64_t expected_groups, int32_t *d_keys, float *d_vals, int64_t cap, int64_t *h_groups);
+
+/* ---- ORDER BY ... [LIMIT k [OFFSET o]]:  jit_sort_float + truncate
+ * (include/jit.hpp:26-27, src/jit.cpp:283-307, src/warpdb.cpp:453-455,483-495).
+ * key_expr orders, val_expr (NULL = key_expr) is returned; ties keep row order (stable).
+ * Writes min(k, survivors - offset) values to d_out_vals / d_out_keys (either may be NULL);
+ * k < 0 means no LIMIT (full sort; d_out must hold n).  Synchronises when h_n != NULL. */
+int wdb_topk(int device, void *stream, const wdb_col_t *cols, int ncols, const char *key_expr,
+             const char *val_expr, const char *cond, int descending, int64_t k, int64_t offset,
+             int64_t n, float *d_out_vals, float *d_out_keys, int64_t *h_n);
+
+/* ---- in-place stable device sorts: jit_sort_float / jit_sort_pairs
+ * (include/jit.hpp:22-27, src/jit.cpp:248-307) */
+int wdb_sort_float(int device, void *stream, float *d_vals, int64_t count, int ascending);
+int wdb_sort_pairs(int device, void *stream, int32_t *d_keys, float *d_vals, int64_t count, int ascending);
+
+/* ---- optimizer support: column statistics (TableStats, include/csv_loader.hpp:22-37) and
+ * zone maps (per-tile min/max) used for pruning; new work, the reference's analyze_condition is
+ * a stub (src/optimizer.cpp:13-17). */
+int wdb_column_minmax(int device, void *stream, const wdb_col_t *col, double *h_min, double *h_max);
+
+/* ---- multi-GPU: run_multi_gpu_jit_host (include/multi_gpu_utils.hpp:10-12,
+ * src/multi_gpu_utils.cpp:5-63).  Host columns in, host floats out; rows are split into
+ * contiguous shards chunk = ceil(n/ndev) and all devices run concurrently on their own
+ * streams (the reference loops over them sequentially).  h_cols[i].dptr are HOST pointers. */
+int wdb_multi_project_filter_host(int ndev, const wdb_col_t *h_cols, int ncols, const char *expr,
+                                  const char *cond, float *h_out, int64_t n, int mode, int64_t *h_count);
+/* shard [start,end) of device dev: src/multi_gpu_utils.cpp:24-31 */
+int wdb_shard_range(int64_t n, int ndev, int dev, int64_t *start, int64_t *end);
+
+/* ---- synthetic columns for benchmarks/tests (counter based, bit-identical to the oracle's
+ * orc_synth_*; not part of the reference) */
+int wdb_synth_f32(int device, void *stream, float *d_out, int64_t n, uint64_t seed, float lo, float hi, int64_t row0);
+int wdb_synth_i32(int device, void *stream, int32_t *d_out, int64_t n, uint64_t seed, int32_t lo, int32_t hi_excl, int64_t row0);
+
+/* ---- introspection for tests: generate (and compile for `arch`, e.g. "sm_100a") the kernel a
+ * call would use, without a device.  kind: "project", "filter", "compact", "group", "topk".
+ * Returns the CUDA source and/or the CUBIN through malloc'd buffers the caller frees with wdb_free. */
+int wdb_debug_compile(const char *kind, const wdb_col_t *cols, int ncols, const char *expr_a,
+                      const char *expr_b, const char *cond, int mode, const char *arch, char **out_source,
+                      void **out_cubin, size_t *out_cubin_size);
+void wdb_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

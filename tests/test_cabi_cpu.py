@@ -1,0 +1,103 @@
+"""CPU: the C-ABI library loads, exports every symbol include/warpcore.h declares, generates and
+compiles its kernel templates for sm_100a offline (NVRTC needs no GPU), and fails loudly when asked
+to compute without a CUDA device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from warpdb_b200 import _core as wc
+from warpdb_b200 import build as wbuild
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCHEMA = [("price", wc.FLOAT32, 0, 0), ("quantity", wc.INT32, 0, 0)]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    wbuild.build()
+
+
+def sass_of(cubin, tmp_path, name="k.cubin"):
+    p = tmp_path / name
+    p.write_bytes(cubin)
+    return subprocess.run(["cuobjdump", "-sass", str(p)], capture_output=True, text=True, check=True).stdout
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "warpcore.h")).read()
+    declared = set(re.findall(r"\b(wdb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(wc.SYMBOLS), declared ^ set(wc.SYMBOLS)
+    L = wc.lib()
+    for s in declared:
+        assert hasattr(L, s), s
+    assert L.wdb_abi_version() == 1
+
+
+def test_shard_range_matches_reference_formula():
+    # src/multi_gpu_utils.cpp:24-31
+    assert [wc.shard_range(10, 4, d) for d in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert [wc.shard_range(4, 8, d) for d in range(8)] == [(0, 1), (1, 2), (2, 3), (3, 4)] + [(4, 4)] * 4
+
+
+def test_project_kernel_is_vectorised_sm100(tmp_path):
+    src, cubin = wc.debug_compile("project", SCHEMA, "((price[idx] * quantity[idx]) * 1.08f)")
+    assert "wdb_cell<wdb_t0> price, wdb_cell<wdb_t1> quantity" in src
+    sass = sass_of(cubin, tmp_path)
+    assert "sm_100a" in sass or "SM100" in sass.upper()
+    assert "LDG.E.NA.ENL2.256.CONSTANT" in sass and "STG.E.ENL2.256" in sass   # 256-bit accesses, new on sm_100
+    assert "FMUL" in sass
+
+
+def test_only_referenced_columns_are_loaded(tmp_path):
+    src, _ = wc.debug_compile("project", SCHEMA, "(price[idx] * 0.9f)", want_cubin=False)
+    assert "#define WDB_NUSED 1" in src and "quantity" not in src.split("---- end UDF ----")[1]
+
+
+def test_compact_kernel_uses_ballot_popc_and_lookback(tmp_path):
+    _, cubin = wc.debug_compile("compact", SCHEMA, "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", wc.COMPACT)
+    sass = sass_of(cubin, tmp_path)
+    assert "VOTE" in sass and "POPC" in sass and "ATOMG" in sass and "LDG.E.64.STRONG.GPU" in sass
+
+
+def test_bulk_variant_emits_tma_bulk_copies(tmp_path):
+    wc.set_option("project.variant", 2)
+    try:
+        _, cubin = wc.debug_compile("project", SCHEMA, "((price[idx] * quantity[idx]) * 1.08f)")
+    finally:
+        wc.set_option("project.variant", 0)
+    sass = sass_of(cubin, tmp_path)
+    assert "UBLKCP" in sass and "SYNCS" in sass
+
+
+def test_udf_source_is_prepended(tmp_path):
+    wc.set_udf_source("__device__ float discount(float price, float rate) {\n    return price * rate;\n}\n")
+    try:
+        src, cubin = wc.debug_compile("project", SCHEMA, "discount(price[idx], 0.9f)")
+    finally:
+        wc.set_udf_source("")
+    assert "__device__ float discount" in src and len(cubin) > 1000
+
+
+def test_compile_error_contract(capfd):
+    # src/jit.cpp:119-129 and tests/jit_error_test.cpp: log on stderr, "Kernel compilation failed."
+    with pytest.raises(wc.WarpcoreError, match=r"Kernel compilation failed\."):
+        wc.debug_compile("project", SCHEMA, "invalid@")
+    assert "NVRTC Compile Log" in capfd.readouterr().err
+    # and the library still works afterwards
+    _, cubin = wc.debug_compile("project", SCHEMA, "(price[idx] + 1.0f)")
+    assert len(cubin) > 1000
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(wc.WarpcoreError, match="no CUDA device|CUDA error"):
+        wc.check(wc.lib().wdb_init(0))
+    cols, n = wc.make_cols(SCHEMA)
+    cnt = C.c_int64(0)
+    rc = wc.lib().wdb_project_filter(0, None, cols, n, b"(price[idx] + 1.0f)", b"", None, 4, 0, None, C.byref(cnt))
+    assert rc != 0

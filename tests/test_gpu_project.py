@@ -1,0 +1,207 @@
+"""GPU parity: fused filter/project/compaction through the C ABI vs the CPU oracle (bit-exact)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import pyoracle as orc
+from warpdb_b200 import _core as wc
+from warpdb_b200 import ops
+
+UDF = "__device__ float discount(float price, float rate) {\n    return price * rate;\n}\n"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def gpu():
+    assert torch.cuda.is_available(), "these tests need the B200"
+    wc.check(wc.lib().wdb_init(0))
+    wc.set_udf_source(UDF)
+    yield
+    wc.set_udf_source("")
+
+
+def dev(table):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in table.items()}
+
+
+def bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def check_dense(table, text, where=None, fill=-123.0):
+    e = orc.Expr(text).cuda()
+    c = orc.Expr(where).cuda() if where else None
+    ref, mask = orc.project_filter(text, where, table, fill=fill)
+    d = dev(table)
+    n = len(ref)
+    out = torch.full((n,), fill, dtype=torch.float32, device="cuda")
+    ops.project_filter(d, e, c, wc.DENSE, out=out)
+    got = out.cpu().numpy()
+    assert np.array_equal(bits(got), bits(ref)), (text, where)
+    # zero-fill mode
+    out0, _ = ops.project_filter(d, e, c, wc.DENSE_ZERO)
+    ref0 = np.where(mask.astype(bool), ref, np.float32(0))
+    assert np.array_equal(bits(out0.cpu().numpy()), bits(ref0)), (text, where)
+    # stable compaction
+    outc, cnt = ops.project_filter(d, e, c, wc.COMPACT)
+    refc = orc.filter_compact(text, where, table)
+    assert cnt == len(refc), (text, where, cnt, len(refc))
+    assert np.array_equal(bits(outc[:cnt].cpu().numpy()), bits(refc)), (text, where)
+
+
+def test_reference_fixture_kats(fixtures):
+    # SURVEY Appendix B / tests/extended_types_test.cpp / tests/jit_arch_test.cpp
+    t = fixtures["test"]
+    out, _ = ops.project_filter(dev(t), "(price[idx] * quantity[idx])", "(price[idx] > 10.0f)")
+    assert [format(int(x), "08x") for x in bits(out.cpu().numpy())] == ["41fc0000", "42a00000", "41f40000", "43160000"]
+    out, _ = ops.project_filter(dev(t), "((price[idx] * quantity[idx]) * 1.08f)")
+    assert [format(int(x), "08x") for x in bits(out.cpu().numpy())] == ["4208147b", "42accccd", "4203c290", "43220000"]
+    out, _ = ops.project_filter(dev(fixtures["extended"]), "(price[idx] * discount[idx])")
+    assert [format(int(x), "08x") for x in bits(out.cpu().numpy())] == ["3f866667", "40800000", "3f433333", "40900000"]
+    one = {"price": np.array([2.0], np.float32), "quantity": np.array([0], np.int32)}
+    out, _ = ops.project_filter(dev(one), "price[idx]")
+    assert out.cpu().tolist() == [2.0]
+
+
+def test_synth_generators_match_oracle():
+    for n, row0 in [(1, 0), (1000, 0), (100003, 12345), (1 << 20, (1 << 33) + 7)]:
+        a = ops.synth_f32(n, 0xC0FFEE, 0.0, 100.0, row0).cpu().numpy()
+        assert np.array_equal(bits(a), bits(orc.synth_f32(n, 0xC0FFEE, 0.0, 100.0, row0)))
+        b = ops.synth_i32(n, 0xC0FFEF, 1, 101, row0).cpu().numpy()
+        assert np.array_equal(b, orc.synth_i32(n, 0xC0FFEF, 1, 101, row0))
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 31, 32, 33, 255, 1023, 4095, 4096, 4097, 8191, 8192, 8193, 100003, 1 << 20])
+def test_ragged_sizes(n):
+    t = {"price": orc.synth_f32(n, 1, 0.0, 40.0), "quantity": orc.synth_i32(n, 2, 1, 101)}
+    if n == 0:
+        d = {k: torch.empty(0, dtype=torch.float32 if k == "price" else torch.int32, device="cuda") for k in t}
+        out, cnt = ops.project_filter(d, "(price[idx] * quantity[idx])", None)
+        assert out.numel() == 0 and cnt == 0
+        out, cnt = ops.project_filter(d, "(price[idx] * 0.9f)", "(price[idx] > 20.0f)", wc.COMPACT)
+        assert cnt == 0
+        return
+    check_dense(t, "price * quantity * 1.08")
+    check_dense(t, "price * 0.9", "price > 20")
+
+
+@pytest.mark.parametrize("text,where", [
+    ("price * quantity * 1.08", None),
+    ("price * 0.9", "price > 20"),
+    ("discount(price, 0.9)", "price > 20 AND quantity < 50"),
+    ("price + quantity * 2", "price > 10 OR quantity < 5"),
+    ("(price + quantity) * 2", "quantity <= 5"),
+    ("price * price + 1", None),                 # fma contraction
+    ("1 - price * quantity", "price != quantity"),
+    ("price * quantity - quantity * 3", None),   # both operands are products
+    ("price / quantity - 2", "quantity >= 2"),
+    ("quantity / quantity2", None),              # int / int
+    ("quantity * quantity2 + quantity", None),   # int arithmetic
+    ("d * 2 + price", "d > 0.5"),                # double column
+    ("l + quantity", "l > 100"),                 # int64 column
+    ("sqrtf(price) + fminf(price, 3)", "fmaxf(price, 20) > 20"),
+    ("price", "price > 100"),                    # nothing survives
+    ("price", "price > 0 OR price == 0"),        # everything survives
+    ("7", None),
+    ("price > 20", None),                        # boolean valued expression
+])
+def test_expression_matrix(text, where):
+    n = 70001
+    t = {"price": orc.synth_f32(n, 3, 0.0, 40.0), "quantity": orc.synth_i32(n, 4, 1, 101),
+         "quantity2": orc.synth_i32(n, 5, 1, 7), "d": orc.synth_f32(n, 6, 0.0, 1.0).astype(np.float64) / 3.0,
+         "l": orc.synth_i32(n, 7, 0, 1000).astype(np.int64) * 1000003}
+    check_dense(t, text, where)
+
+
+@pytest.mark.parametrize("sel", [0.0, 0.01, 0.5, 0.99, 1.0])
+def test_compaction_selectivities(sel):
+    n = 3_000_017
+    hi = 20.0 / (1.0 - sel) if sel < 1.0 else 10.0
+    lo = 0.0 if sel > 0 else 0.0
+    if sel == 0.0:
+        hi = 20.0
+    if sel == 1.0:
+        lo, hi = 21.0, 40.0
+    t = {"price": orc.synth_f32(n, 9, lo, hi)}
+    ref = orc.filter_compact("price * 0.9", "price > 20", t)
+    out, cnt = ops.project_filter(dev(t), "(price[idx] * 0.9f)", "(price[idx] > 20.0f)", wc.COMPACT)
+    assert cnt == len(ref)
+    assert abs(cnt / n - sel) < 0.01
+    assert np.array_equal(bits(out[:cnt].cpu().numpy()), bits(ref))
+
+
+def test_misaligned_columns_take_the_scalar_path():
+    n = 50001
+    p = orc.synth_f32(n + 3, 10, 0.0, 40.0)
+    dp = torch.from_numpy(p).cuda()
+    for off in (1, 2, 3):
+        t = {"price": p[off:off + n]}
+        d = {"price": dp[off:off + n]}
+        ref, _ = orc.project_filter("price * 0.9", "price > 20", t, fill=0.0)
+        out, _ = ops.project_filter(d, "(price[idx] * 0.9f)", "(price[idx] > 20.0f)", wc.DENSE_ZERO)
+        assert np.array_equal(bits(out.cpu().numpy()), bits(ref))
+        outc, cnt = ops.project_filter(d, "(price[idx] * 0.9f)", "(price[idx] > 20.0f)", wc.COMPACT)
+        assert np.array_equal(bits(outc[:cnt].cpu().numpy()), bits(orc.filter_compact("price * 0.9", "price > 20", t)))
+
+
+@pytest.mark.parametrize("variant,vec,unroll,block", [(0, 4, 1, 128), (0, 8, 4, 256), (1, 8, 2, 512), (1, 4, 8, 256), (2, 4, 4, 256)])
+def test_kernel_variants_agree(variant, vec, unroll, block):
+    n = 1_000_003
+    t = {"price": orc.synth_f32(n, 11, 0.0, 100.0), "quantity": orc.synth_i32(n, 12, 1, 101)}
+    ref, _ = orc.project_filter("price * quantity * 1.08", None, t)
+    ref0, m0 = orc.project_filter("price * 0.9", "price > 20", t, fill=0.0)
+    d = dev(t)
+    opts = {"project.variant": variant, "project.vec": vec, "project.unroll": unroll, "project.block": block}
+    try:
+        for k, v in opts.items():
+            wc.set_option(k, v)
+        out, _ = ops.project_filter(d, "((price[idx] * quantity[idx]) * 1.08f)")
+        assert np.array_equal(bits(out.cpu().numpy()), bits(ref))
+        out, _ = ops.project_filter(d, "(price[idx] * 0.9f)", "(price[idx] > 20.0f)", wc.DENSE_ZERO)
+        assert np.array_equal(bits(out.cpu().numpy()), bits(ref0))
+    finally:
+        for k, v in {"project.variant": 0, "project.vec": 8, "project.unroll": 4, "project.block": 256}.items():
+            wc.set_option(k, v)
+
+
+def test_compile_error_and_recovery():
+    # tests/jit_error_test.cpp:19-33
+    d = dev({"price": np.array([1.0], np.float32), "quantity": np.array([1], np.int32)})
+    with pytest.raises(wc.WarpcoreError, match=r"Kernel compilation failed\."):
+        ops.project_filter(d, "invalid@")
+    out, _ = ops.project_filter(d, "(price[idx] + 1.0f)")
+    assert out.cpu().tolist() == [2.0]
+
+
+def test_kernel_cache_hits():
+    d = dev({"price": orc.synth_f32(1000, 1, 0.0, 1.0)})
+    ops.project_filter(d, "(price[idx] * 3.25f)")
+    s0 = wc.stats()
+    ops.project_filter(d, "(price[idx] * 3.25f)")
+    s1 = wc.stats()
+    assert s1["kernels_compiled"] == s0["kernels_compiled"] and s1["cache_hits"] == s0["cache_hits"] + 1
+    assert s1["launches"] > s0["launches"]
+
+
+def test_full_size_properties_config2_and_3():
+    """BASELINE configs 2/3 at a quarter of full size (2.5e8 / 1e9 rows): size-independent checks."""
+    n = 250_000_000
+    price = ops.synth_f32(n, 0xC0FFEE + 2, 0.0, 100.0)
+    qty = ops.synth_i32(n, 0xC0FFEE + 102, 1, 101)
+    out, _ = ops.project_filter({"price": price, "quantity": qty}, "((price[idx] * quantity[idx]) * 1.08f)")
+    ref = (price * qty.to(torch.float32)) * 1.08            # torch fp32: same two roundings
+    assert torch.equal(out, ref)
+    # head and tail windows against the oracle (counter-based generator regenerates any window)
+    for row0 in (0, n - 100000):
+        t = {"price": orc.synth_f32(100000, 0xC0FFEE + 2, 0.0, 100.0, row0), "quantity": orc.synth_i32(100000, 0xC0FFEE + 102, 1, 101, row0)}
+        r, _ = orc.project_filter("price * quantity * 1.08", None, t)
+        assert np.array_equal(bits(out[row0:row0 + 100000].cpu().numpy()), bits(r))
+    del out, ref, qty
+    n = 1_000_000_000
+    price = ops.synth_f32(n, 0xC0FFEE + 3, 0.0, 40.0)
+    outc, cnt = ops.project_filter({"price": price}, "(price[idx] * 0.9f)", "(price[idx] > 20.0f)", wc.COMPACT)
+    mask = price > 20.0
+    assert cnt == int(mask.sum().item())
+    assert torch.equal(outc[:cnt], (price[mask] * 0.9))     # stable order: equals masked_select order

@@ -1,0 +1,189 @@
+// compact.cuh -- fused filter + project + STABLE stream compaction in one pass.
+//
+// The reference never compacts on the GPU; row-order compaction exists only in the
+// host half of query_sql (src/warpdb.cpp:336-344,457-459).  Here every CTA takes tiles in ticket
+// order, evaluates cond/expr on WDB_VEC-wide vector loads, ranks survivors with warp ballots +
+// popc (no shuffles), stages them in shared memory in row order and obtains its global offset with
+// a decoupled look-back over 64-bit tile status words, so the packed output is written once, fully
+// coalesced and in row order.
+//
+// Roofline: HBM.  Algorithmic bytes per row = sum(sizeof used columns) + 4*WDB_NOUT*selectivity.
+//
+// Host-supplied macros: WDB_BLOCK, WDB_UNROLL (slabs per warp per tile), WDB_VEC, WDB_NOUT (1|2),
+// generated WDB_COND, WDB_EXPR and (NOUT==2) WDB_EXPR2.
+#define WDB_NWARPS (WDB_BLOCK / 32)
+#define WDB_SLAB_ROWS (32 * WDB_VEC)
+#define WDB_WARP_ROWS (WDB_SLAB_ROWS * WDB_UNROLL)
+#define WDB_TILE_ROWS (WDB_WARP_ROWS * WDB_NWARPS)
+
+#define WDB_ST_AGG 1ull
+#define WDB_ST_PREFIX 2ull
+#define WDB_ST_MASK ((1ull << 62) - 1ull)
+
+__device__ __forceinline__ u64 wdb_ld_status(const u64 *p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wdb_st_status(u64 *p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 wdb_warp_sum64(u64 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(WDB_FULL_MASK, v, o);
+  return v;
+}
+
+extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
+wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n,
+            u64 *__restrict__ status, u32 *__restrict__ ticket, i64 *__restrict__ out_count, const i64 ntiles) {
+  __shared__ float s_stage[WDB_TILE_ROWS];
+#if WDB_NOUT == 2
+  __shared__ float s_stage2[WDB_TILE_ROWS];
+#endif
+  __shared__ u32 s_wcount[WDB_NWARPS];
+  __shared__ i64 s_base;
+  __shared__ u32 s_tile;
+  const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const u32 lt = wdb_lanemask_lt();
+
+  while (true) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();                                            // (1)
+    const i64 tile = (i64)s_tile;
+    if (tile >= ntiles) break;
+    const i64 wrow0 = tile * WDB_TILE_ROWS + (i64)warp * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
+
+    u32 flags[WDB_UNROLL];
+    float vals[WDB_UNROLL][WDB_VEC];
+#if WDB_NOUT == 2
+    float vals2[WDB_UNROLL][WDB_VEC];
+#endif
+    if ((tile + 1) * WDB_TILE_ROWS <= n) {
+      wdb_rows R[WDB_UNROLL];
+#pragma unroll
+      for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows(C, wrow0 + (i64)u * WDB_SLAB_ROWS, R[u]);
+#pragma unroll
+      for (int u = 0; u < WDB_UNROLL; ++u) {
+        u32 m = 0;
+#pragma unroll
+        for (int j = 0; j < WDB_VEC; ++j) {
+          m |= (WDB_COND(R[u], j) ? 1u : 0u) << j;
+          vals[u][j] = WDB_EXPR(R[u], j);
+#if WDB_NOUT == 2
+          vals2[u][j] = WDB_EXPR2(R[u], j);
+#endif
+        }
+        flags[u] = m;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < WDB_UNROLL; ++u) {
+        u32 m = 0;
+#pragma unroll
+        for (int j = 0; j < WDB_VEC; ++j) {
+          const i64 row = wrow0 + (i64)u * WDB_SLAB_ROWS + j;
+          vals[u][j] = 0.0f;
+#if WDB_NOUT == 2
+          vals2[u][j] = 0.0f;
+#endif
+          if (row < n) {
+            wdb_rows R;
+            wdb_load_row1(C, row, R, 0);
+            if (WDB_COND(R, 0)) {
+              m |= 1u << j;
+              vals[u][j] = WDB_EXPR(R, 0);
+#if WDB_NOUT == 2
+              vals2[u][j] = WDB_EXPR2(R, 0);
+#endif
+            }
+          }
+        }
+        flags[u] = m;
+      }
+    }
+
+    // rank of this lane's first survivor inside the warp's region: ballots give, per element slot
+    // j, the set of lanes that keep it; rows are ordered (slab, lane, j)
+    u32 rank[WDB_UNROLL], wtotal = 0;
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) {
+      u32 pre = 0, tot = 0;
+#pragma unroll
+      for (int j = 0; j < WDB_VEC; ++j) {
+        const u32 b = __ballot_sync(WDB_FULL_MASK, (flags[u] >> j) & 1u);
+        pre += __popc(b & lt);
+        tot += __popc(b);
+      }
+      rank[u] = wtotal + pre;
+      wtotal += tot;
+    }
+    if (lane == 0) s_wcount[warp] = wtotal;
+    __syncthreads();                                            // (2)
+    u32 woff = 0, ttotal = 0;
+#pragma unroll
+    for (int w = 0; w < WDB_NWARPS; ++w) {
+      const u32 c = s_wcount[w];
+      woff += (w < (int)warp) ? c : 0u;
+      ttotal += c;
+    }
+
+    if (warp == 0) {  // decoupled look-back
+      i64 excl = 0;
+      if (tile == 0) {
+        if (lane == 0) wdb_st_status(&status[0], (WDB_ST_PREFIX << 62) | (u64)ttotal);
+      } else {
+        if (lane == 0) wdb_st_status(&status[tile], (WDB_ST_AGG << 62) | (u64)ttotal);
+        i64 look = tile - 1;
+        while (true) {
+          const i64 idx = look - (i64)lane;
+          u64 st = (WDB_ST_PREFIX << 62);
+          if (idx >= 0) {
+            do { st = wdb_ld_status(&status[idx]); } while ((st >> 62) == 0ull);
+          }
+          const u32 pm = __ballot_sync(WDB_FULL_MASK, (st >> 62) == WDB_ST_PREFIX);
+          const u64 v = st & WDB_ST_MASK;
+          if (pm) {
+            const u32 first = (u32)__ffs((int)pm) - 1u;
+            excl += (i64)wdb_warp_sum64(lane <= first ? v : 0ull);
+            break;
+          }
+          excl += (i64)wdb_warp_sum64(v);
+          look -= 32;
+        }
+        if (lane == 0) wdb_st_status(&status[tile], (WDB_ST_PREFIX << 62) | (u64)(excl + (i64)ttotal));
+      }
+      if (lane == 0) {
+        s_base = excl;
+        if (tile == ntiles - 1) *out_count = excl + (i64)ttotal;
+      }
+    }
+
+    // stage survivors in row order
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) {
+      u32 pos = woff + rank[u];
+#pragma unroll
+      for (int j = 0; j < WDB_VEC; ++j)
+        if ((flags[u] >> j) & 1u) {
+          s_stage[pos] = vals[u][j];
+#if WDB_NOUT == 2
+          s_stage2[pos] = vals2[u][j];
+#endif
+          ++pos;
+        }
+    }
+    __syncthreads();                                            // (3)
+    const i64 g0 = s_base;
+    // copy out with warps writing 128-byte aligned spans of the destination
+    const int mis = (int)(g0 & 31);
+    for (int i = (int)threadIdx.x - mis; i < (int)ttotal; i += WDB_BLOCK)
+      if (i >= 0) {
+        out[g0 + i] = s_stage[i];
+#if WDB_NOUT == 2
+        out2[g0 + i] = s_stage2[i];
+#endif
+      }
+    // the barriers (1) and (2) of the next iteration order these reads before the next staging
+  }
+}

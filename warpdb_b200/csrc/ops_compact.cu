@@ -1,0 +1,87 @@
+// ops_compact.cu -- host side of the single-pass stable compaction (kernels/compact.cuh).
+#include <algorithm>
+
+#include "core.hpp"
+
+namespace wdb {
+
+struct CompactPlan { GenSpec spec; int block, unroll, vec; int64_t tile_rows; bool two; };
+
+static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, const char *expr2, const char *cond,
+                        bool check_alignment, CompactPlan *p) {
+  GenSpec &spec = p->spec;
+  spec.kind = "compact";
+  if (!cond || !*cond) cond = "true";
+  const bool two = expr2 && *expr2;
+  p->two = two;
+  spec.used = find_used_columns(cols, ncols, {expr, two ? expr2 : "", cond});
+  for (const auto &u : spec.used)
+    if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
+  const int block = (int)opt("compact.block", 256), unroll = (int)opt("compact.unroll", 4), vec = (int)opt("compact.vec", 4);
+  if (vec != 4 && vec != 8) return fail("compact.vec must be 4 or 8");
+  if (block < 32 || block > 1024 || (block & 31)) return fail("compact.block must be a multiple of 32 in [32,1024]");
+  if (unroll < 1 || unroll > 8) return fail("compact.unroll must be in [1,8]");
+  p->block = block; p->unroll = unroll; p->vec = vec;
+  p->tile_rows = (int64_t)block * vec * unroll;
+  if (p->tile_rows * 4 * (two ? 2 : 1) > 46 * 1024) return fail("compact tile of %lld rows does not fit static shared memory", (long long)p->tile_rows);
+  const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)vec * 4);
+  spec.defines = {{"WDB_VEC", vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("compact.ld_hint", 0)},
+                  {"WDB_ST_HINT", 0}, {"WDB_BLOCK", block}, {"WDB_UNROLL", unroll}, {"WDB_NOUT", two ? 2 : 1}};
+  spec.fns.push_back({"expr", "float", expr});
+  if (two) spec.fns.push_back({"expr2", "float", expr2});
+  spec.fns.push_back({"cond", "bool", cond});
+  spec.bodies = {k_src_compact};
+  return 0;
+}
+
+int gen_compact_source(const wdb_col_t *cols, int ncols, const char *expr, const char *expr2, const char *cond,
+                       bool assume_aligned, std::string *src) {
+  CompactPlan p;
+  if (plan_compact(cols, ncols, expr, expr2, cond, !assume_aligned, &p)) return 1;
+  *src = gen_source(p.spec);
+  return 0;
+}
+
+int run_compact(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr, const char *expr2,
+                const char *cond, float *d_out, float *d_out2, int64_t n, int64_t *d_count, int64_t *h_count) {
+  CompactPlan p;
+  if (plan_compact(cols, ncols, expr, expr2, cond, true, &p)) return 1;
+  GenSpec &spec = p.spec;
+  const int block = p.block;
+  const int64_t tile_rows = p.tile_rows;
+  Kernel k;
+  if (get_kernel(d, gen_source(spec), "wdb_compact.cu", "wdb_compact", &k)) return 1;
+
+  const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
+  // scratch: [0,8) survivor count, [8,12) ticket, [64, 64+8*ntiles) tile status words
+  const size_t need = 64 + (size_t)std::max<int64_t>(ntiles, 1) * 8;
+  if (ensure_scratch(d, need)) return 1;
+  char *sc = (char *)d->scratch;
+  WDB_CUDA(cudaMemsetAsync(sc, 0, need, stream));
+  long long *d_cnt = (long long *)sc;
+  unsigned *d_ticket = (unsigned *)(sc + 8);
+  unsigned long long *d_status = (unsigned long long *)(sc + 64);
+  if (ntiles > 0) {
+    if (!k.max_ctas_per_sm) {
+      int nb = 0;
+      WDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)k.fn, block, 0));
+      k.max_ctas_per_sm = std::max(nb, 1);
+    }
+    int64_t per_sm = std::min<int64_t>(k.max_ctas_per_sm, opt("compact.ctas_per_sm", 8));
+    unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)d->num_sms * per_sm);
+    std::vector<const void *> ptrs;
+    for (const auto &u : spec.used) ptrs.push_back(cols[u.table_index].dptr);
+    if (ptrs.empty()) ptrs.push_back(nullptr);
+    long long nn = n, nt = ntiles;
+    void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_ticket, &d_cnt, &nt};
+    if (launch(k, grid, block, 0, stream, args)) return 1;
+  }
+  if (d_count) WDB_CUDA(cudaMemcpyAsync(d_count, d_cnt, 8, cudaMemcpyDeviceToDevice, stream));
+  if (h_count) {
+    WDB_CUDA(cudaMemcpyAsync(h_count, d_cnt, 8, cudaMemcpyDeviceToHost, stream));
+    WDB_CUDA(cudaStreamSynchronize(stream));
+  }
+  return 0;
+}
+
+}  // namespace wdb
