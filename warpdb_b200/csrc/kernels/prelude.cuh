@@ -140,11 +140,11 @@ __device__ __forceinline__ void wdb_mbar_wait(u64 *bar, u32 parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WDB_WAIT_%=:\n"
+      "WDB_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WDB_DONE_%=;\n"
-      "bra WDB_WAIT_%=;\n"
-      "WDB_DONE_%=:\n"
+      "@p bra WDB_DONE;\n"
+      "bra WDB_WAIT;\n"
+      "WDB_DONE:\n"
       "}\n" :: "r"(wdb_smem_addr(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void wdb_fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <iostream>
 #include <sstream>
 
@@ -237,35 +238,87 @@ std::string gen_source(const GenSpec &spec) {
 // ------------------------------------------------------------------------------------------------
 // NVRTC
 // ------------------------------------------------------------------------------------------------
+// NVRTC is loaded with dlopen from the CUDA 12.9 toolkit by absolute path: a process that imported
+// PyTorch already has torch's own libnvrtc.so.12 (12.8) mapped under the same soname, and that one
+// predates the 256-bit ld/st PTX (ptxas: "Illegal vector size: 8").
+struct Nvrtc {
+  void *h = nullptr;
+  int major = 0, minor = 0;
+  nvrtcResult (*CreateProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char *const *) = nullptr;
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t *) = nullptr;
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char *) = nullptr;
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t *) = nullptr;
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char *) = nullptr;
+  nvrtcResult (*DestroyProgram)(nvrtcProgram *) = nullptr;
+  const char *(*GetErrorString)(nvrtcResult) = nullptr;
+  nvrtcResult (*Version)(int *, int *) = nullptr;
+};
+static Nvrtc g_nvrtc;
+static int load_nvrtc() {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> l(mu);
+  if (g_nvrtc.h) return 0;
+  std::vector<std::string> cand;
+  if (const char *e = getenv("WARPDB_NVRTC")) cand.push_back(e);
+  if (const char *e = getenv("CUDA_HOME")) cand.push_back(std::string(e) + "/lib64/libnvrtc.so.12");
+  cand.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+  cand.push_back("/usr/local/cuda-12.9/lib64/libnvrtc.so.12");
+  cand.push_back("libnvrtc.so.12");
+  std::string tried;
+  for (const auto &c : cand) {
+    void *h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!h) { tried += c + " "; continue; }
+    Nvrtc n;
+    n.h = h;
+#define WDB_SYM(f) *(void **)(&n.f) = dlsym(h, "nvrtc" #f)
+    WDB_SYM(CreateProgram); WDB_SYM(CompileProgram); WDB_SYM(GetProgramLogSize); WDB_SYM(GetProgramLog);
+    WDB_SYM(GetCUBINSize); WDB_SYM(GetCUBIN); WDB_SYM(DestroyProgram); WDB_SYM(GetErrorString); WDB_SYM(Version);
+#undef WDB_SYM
+    if (!n.CreateProgram || !n.CompileProgram || !n.GetCUBIN || !n.Version) { tried += c + "(symbols) "; dlclose(h); continue; }
+    n.Version(&n.major, &n.minor);
+    if (n.major < 12 || (n.major == 12 && n.minor < 9)) {  // sm_100a + 256-bit ld/st need the 12.9 compiler
+      tried += c + "(" + std::to_string(n.major) + "." + std::to_string(n.minor) + " < 12.9) ";
+      dlclose(h);
+      continue;
+    }
+    g_nvrtc = n;
+    return 0;
+  }
+  return fail("NVRTC error: no NVRTC >= 12.9 found (tried: %s)", tried.c_str());
+}
+
 int compile_to_cubin(const std::string &source, const std::string &name, const std::string &arch, std::string *cubin) {
+  if (load_nvrtc()) return 1;
+  const Nvrtc &N = g_nvrtc;
   nvrtcProgram prog = nullptr;
-  nvrtcResult r = nvrtcCreateProgram(&prog, source.c_str(), name.c_str(), 0, nullptr, nullptr);
-  if (r != NVRTC_SUCCESS) return fail("NVRTC error: %s", nvrtcGetErrorString(r));
+  nvrtcResult r = N.CreateProgram(&prog, source.c_str(), name.c_str(), 0, nullptr, nullptr);
+  if (r != NVRTC_SUCCESS) return fail("NVRTC error: %s", N.GetErrorString(r));
   std::string arch_flag = "--gpu-architecture=" + arch;
   // The reference passes only the architecture (src/jit.cpp:114-117), i.e. NVRTC defaults:
   // --fmad=true, IEEE division and sqrt, no flush-to-zero.  We add the language level, line info
   // for ncu's source page and silence the unused-variable remarks of generated code.
   const char *opts[] = {arch_flag.c_str(), "--std=c++17", "-lineinfo", "-w"};
-  r = nvrtcCompileProgram(prog, 4, opts);
+  r = N.CompileProgram(prog, 4, opts);
   if (r != NVRTC_SUCCESS) {
     size_t n = 0;
-    nvrtcGetProgramLogSize(prog, &n);
+    N.GetProgramLogSize(prog, &n);
     std::string log(n, '\0');
-    nvrtcGetProgramLog(prog, &log[0]);
+    N.GetProgramLog(prog, &log[0]);
     std::cerr << "NVRTC Compile Log:\n" << log << "\n";  // src/jit.cpp:123-125
-    nvrtcDestroyProgram(&prog);
+    N.DestroyProgram(&prog);
     if (getenv("WARPDB_DUMP_SOURCE")) std::cerr << source << "\n";
     return fail("Kernel compilation failed.");            // src/jit.cpp:128
   }
   size_t n = 0;
-  r = nvrtcGetCUBINSize(prog, &n);
+  r = N.GetCUBINSize(prog, &n);
   if (r != NVRTC_SUCCESS || n == 0) {
-    nvrtcDestroyProgram(&prog);
-    return fail("NVRTC error: no CUBIN produced for %s (%s)", arch.c_str(), nvrtcGetErrorString(r));
+    N.DestroyProgram(&prog);
+    return fail("NVRTC error: no CUBIN produced for %s (%s)", arch.c_str(), N.GetErrorString(r));
   }
   cubin->resize(n);
-  nvrtcGetCUBIN(prog, &(*cubin)[0]);
-  nvrtcDestroyProgram(&prog);
+  N.GetCUBIN(prog, &(*cubin)[0]);
+  N.DestroyProgram(&prog);
   return 0;
 }
 
