@@ -162,7 +162,7 @@ def test_kernel_variants_agree(variant, vec, unroll, block):
         out, _ = ops.project_filter(d, "(price[idx] * 0.9f)", "(price[idx] > 20.0f)", wc.DENSE_ZERO)
         assert np.array_equal(bits(out.cpu().numpy()), bits(ref0))
     finally:
-        for k, v in {"project.variant": 0, "project.vec": 8, "project.unroll": 4, "project.block": 256}.items():
+        for k, v in {"project.variant": 0, "project.vec": 8, "project.unroll": 2, "project.block": 512}.items():
             wc.set_option(k, v)
 
 

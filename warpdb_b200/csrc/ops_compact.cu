@@ -17,7 +17,7 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
   spec.used = find_used_columns(cols, ncols, {expr, two ? expr2 : "", cond});
   for (const auto &u : spec.used)
     if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
-  const int block = (int)opt("compact.block", 256), unroll = (int)opt("compact.unroll", 4), vec = (int)opt("compact.vec", 4);
+  const int block = (int)opt("compact.block", 256), unroll = (int)opt("compact.unroll", 4), vec = (int)opt("compact.vec", 8);
   if (vec != 4 && vec != 8) return fail("compact.vec must be 4 or 8");
   if (block < 32 || block > 1024 || (block & 31)) return fail("compact.block must be a multiple of 32 in [32,1024]");
   if (unroll < 1 || unroll > 8) return fail("compact.unroll must be in [1,8]");

@@ -1,0 +1,243 @@
+// ops_sort.cu -- stable LSD radix sort on the device (8-bit digits), the building block behind
+//   wdb_sort_float / wdb_sort_pairs   (replace the <<<1,1>>> bubble sorts of src/jit.cpp:248-307)
+//   key-ordered export of GROUP BY tables and the ORDER BY ... LIMIT candidate sort.
+// Stability matters: the reference's bubble sorts only swap strictly out-of-order neighbours, so
+// equal keys keep their original order in both directions; descending order is obtained by
+// complementing the key, which keeps the LSD passes stable.
+//
+// Three kernels per digit pass: per-chunk digit histogram -> exclusive scan of the
+// (digit-major) chunk histograms -> stable scatter with warp-ballot ranking.  Memory bound:
+// 2 reads + 1 write of the keys (and payloads) per pass.
+#include <algorithm>
+
+#include "core.hpp"
+
+namespace wdb {
+
+constexpr int kSortBlock = 256;
+constexpr int kSortWarps = kSortBlock / 32;
+
+template <class K> __device__ __forceinline__ unsigned digit_of(K key, int shift) { return (unsigned)(key >> shift) & 255u; }
+
+template <class K>
+__global__ void __launch_bounds__(kSortBlock) sort_hist_kernel(const K *__restrict__ keys, long long n, long long chunk, int shift,
+                                                               unsigned *__restrict__ hist /* [256][nchunks] */, long long nchunks) {
+  __shared__ unsigned s_hist[256];
+  s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const long long begin = (long long)blockIdx.x * chunk, end = min(begin + chunk, n);
+  for (long long i = begin + threadIdx.x; i < end; i += kSortBlock) atomicAdd(&s_hist[digit_of(keys[i], shift)], 1u);
+  __syncthreads();
+  hist[(long long)threadIdx.x * nchunks + blockIdx.x] = s_hist[threadIdx.x];
+}
+
+// exclusive scan of `m` counters into 64-bit offsets, one block
+__global__ void __launch_bounds__(1024) sort_scan_kernel(const unsigned *__restrict__ hist, long long *__restrict__ offs, long long m) {
+  __shared__ long long s_part[1024];
+  const long long per = (m + 1023) / 1024;
+  const long long b = (long long)threadIdx.x * per, e = min(b + per, m);
+  long long sum = 0;
+  for (long long i = b; i < e; ++i) sum += hist[i];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    for (int i = 0; i < 1024; ++i) { long long t = s_part[i]; s_part[i] = run; run += t; }
+  }
+  __syncthreads();
+  long long run = s_part[threadIdx.x];
+  for (long long i = b; i < e; ++i) { offs[i] = run; run += hist[i]; }
+}
+
+template <class K, bool HAS_PAYLOAD>
+__global__ void __launch_bounds__(kSortBlock) sort_scatter_kernel(const K *__restrict__ keys_in, K *__restrict__ keys_out,
+                                                                  const unsigned *__restrict__ pay_in, unsigned *__restrict__ pay_out,
+                                                                  long long n, long long chunk, int shift,
+                                                                  const long long *__restrict__ offs, long long nchunks) {
+  __shared__ long long s_base[256];                 // running output offset per digit for this chunk
+  __shared__ unsigned s_wcount[kSortWarps][256];    // per-warp digit counts of the current round
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  s_base[threadIdx.x] = offs[(long long)threadIdx.x * nchunks + blockIdx.x];
+  const long long begin = (long long)blockIdx.x * chunk, end = min(begin + chunk, n);
+  for (long long r0 = begin; r0 < end; r0 += kSortBlock) {
+    for (int w = 0; w < kSortWarps; ++w) s_wcount[w][threadIdx.x] = 0;
+    __syncthreads();
+    const long long i = r0 + threadIdx.x;
+    const bool valid = i < end;
+    K key = 0;
+    unsigned pay = 0;
+    if (valid) { key = keys_in[i]; if (HAS_PAYLOAD) pay = pay_in[i]; }
+    const unsigned d = digit_of(key, shift);
+    // lanes of this warp holding the same digit (8 ballots); invalid lanes form their own class
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+    if (!valid) peers = ~peers;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+      peers &= ((d >> b) & 1u) ? bal : ~bal;
+    }
+    const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) s_wcount[warp][d] = __popc(peers);
+    __syncthreads();
+    // digit `threadIdx.x`: turn per-warp counts into exclusive prefixes, advance the chunk offset
+    {
+      unsigned run = 0;
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) { const unsigned c = s_wcount[w][threadIdx.x]; s_wcount[w][threadIdx.x] = run; run += c; }
+      // stash the round total in the high half so the base can be advanced after use
+      s_wcount[0][threadIdx.x] |= 0;  // (kept for clarity)
+      __syncthreads();
+      if (valid) {
+        const long long pos = s_base[d] + s_wcount[warp][d] + rank;
+        keys_out[pos] = key;
+        if (HAS_PAYLOAD) pay_out[pos] = pay;
+      }
+      __syncthreads();
+      s_base[threadIdx.x] += run;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- key transforms ----------------------------------------------------------------------------
+// float -> u32 that sorts like the float (NaN-free inputs; -0 sorts before +0)
+__device__ __forceinline__ unsigned f32_to_ordered(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_f32(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__global__ void f32_encode_kernel(const float *__restrict__ in, unsigned *__restrict__ out, long long n, int descending) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned k = f32_to_ordered(in[i]);
+    out[i] = descending ? ~k : k;
+  }
+}
+__global__ void f32_decode_kernel(const unsigned *__restrict__ in, float *__restrict__ out, long long n, int descending) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned k = in[i];
+    out[i] = ordered_to_f32(descending ? ~k : k);
+  }
+}
+__global__ void i32_encode_kernel(const int *__restrict__ in, unsigned *__restrict__ out, long long n, int descending) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned k = (unsigned)in[i] ^ 0x80000000u;
+    out[i] = descending ? ~k : k;
+  }
+}
+__global__ void i32_decode_kernel(const unsigned *__restrict__ in, int *__restrict__ out, long long n, int descending) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned k = in[i];
+    out[i] = (int)((descending ? ~k : k) ^ 0x80000000u);
+  }
+}
+__global__ void iota_kernel(unsigned *__restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = (unsigned)i;
+}
+__global__ void gather_f32_kernel(const float *__restrict__ in, const unsigned *__restrict__ idx, float *__restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = in[idx[i]];
+}
+
+static unsigned grid_for(Device *d, long long n) {
+  return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)d->num_sms * 16));
+}
+
+// Stable ascending sort of n keys (and optional 32-bit payloads).  keys/pay are sorted in place;
+// tmp_keys/tmp_pay are same-sized scratch.  key_bits selects the number of 8-bit passes.
+template <class K>
+int radix_sort(Device *d, cudaStream_t s, K *keys, K *tmp_keys, unsigned *pay, unsigned *tmp_pay, long long n, int key_bits) {
+  if (n <= 1) return 0;
+  long long chunk = 4096;
+  while ((n + chunk - 1) / chunk > 65536) chunk *= 2;
+  const long long nchunks = (n + chunk - 1) / chunk;
+  const size_t hist_bytes = sizeof(unsigned) * 256 * (size_t)nchunks, offs_bytes = sizeof(long long) * 256 * (size_t)nchunks;
+  void *hist = nullptr;
+  WDB_CUDA(cudaMallocAsync(&hist, hist_bytes + offs_bytes, s));
+  unsigned *d_hist = (unsigned *)hist;
+  long long *d_offs = (long long *)((char *)hist + hist_bytes);
+  K *src = keys, *dst = tmp_keys;
+  unsigned *psrc = pay, *pdst = tmp_pay;
+  const int passes = key_bits / 8;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    sort_hist_kernel<K><<<(unsigned)nchunks, kSortBlock, 0, s>>>(src, n, chunk, shift, d_hist, nchunks);
+    sort_scan_kernel<<<1, 1024, 0, s>>>(d_hist, d_offs, 256 * nchunks);
+    if (pay) sort_scatter_kernel<K, true><<<(unsigned)nchunks, kSortBlock, 0, s>>>(src, dst, psrc, pdst, n, chunk, shift, d_offs, nchunks);
+    else sort_scatter_kernel<K, false><<<(unsigned)nchunks, kSortBlock, 0, s>>>(src, dst, nullptr, nullptr, n, chunk, shift, d_offs, nchunks);
+    stats().launches += 3;
+    std::swap(src, dst);
+    std::swap(psrc, pdst);
+  }
+  WDB_CUDA(cudaGetLastError());
+  if (src != keys) {  // odd number of passes: result sits in the scratch buffers
+    WDB_CUDA(cudaMemcpyAsync(keys, src, sizeof(K) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    if (pay) WDB_CUDA(cudaMemcpyAsync(pay, psrc, sizeof(unsigned) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+  }
+  WDB_CUDA(cudaFreeAsync(hist, s));
+  return 0;
+}
+template int radix_sort<unsigned>(Device *, cudaStream_t, unsigned *, unsigned *, unsigned *, unsigned *, long long, int);
+template int radix_sort<unsigned long long>(Device *, cudaStream_t, unsigned long long *, unsigned long long *, unsigned *, unsigned *, long long, int);
+
+// sort floats in place (optionally carrying a float payload that is permuted alongside)
+int sort_f32(Device *d, cudaStream_t s, float *d_keys, float *d_payload, long long n, bool ascending) {
+  if (n <= 1) return 0;
+  const size_t nb = sizeof(unsigned) * (size_t)n;
+  char *buf = nullptr;
+  WDB_CUDA(cudaMallocAsync((void **)&buf, nb * (d_payload ? 5 : 2), s));
+  unsigned *k = (unsigned *)buf, *kt = (unsigned *)(buf + nb);
+  unsigned *p = d_payload ? (unsigned *)(buf + 2 * nb) : nullptr, *pt = d_payload ? (unsigned *)(buf + 3 * nb) : nullptr;
+  float *pv = d_payload ? (float *)(buf + 4 * nb) : nullptr;
+  const unsigned g = grid_for(d, n);
+  f32_encode_kernel<<<g, 256, 0, s>>>(d_keys, k, n, ascending ? 0 : 1);
+  if (d_payload) iota_kernel<<<g, 256, 0, s>>>(p, n);
+  if (radix_sort<unsigned>(d, s, k, kt, p, pt, n, 32)) return 1;
+  f32_decode_kernel<<<g, 256, 0, s>>>(k, d_keys, n, ascending ? 0 : 1);
+  if (d_payload) {
+    gather_f32_kernel<<<g, 256, 0, s>>>(d_payload, p, pv, n);
+    WDB_CUDA(cudaMemcpyAsync(d_payload, pv, nb, cudaMemcpyDeviceToDevice, s));
+  }
+  stats().launches += d_payload ? 4 : 2;
+  WDB_CUDA(cudaGetLastError());
+  WDB_CUDA(cudaFreeAsync(buf, s));
+  return 0;
+}
+
+}  // namespace wdb
+
+using namespace wdb;
+
+extern "C" {
+
+// jit_sort_float (include/jit.hpp:26-27, src/jit.cpp:283-307)
+int wdb_sort_float(int device, void *stream, float *d_vals, int64_t count, int ascending) {
+  Device *d;
+  if (get_device(device, &d)) return 1;
+  if (count < 0) return fail("negative count");
+  return sort_f32(d, (cudaStream_t)stream, d_vals, nullptr, count, ascending != 0);
+}
+
+// jit_sort_pairs (include/jit.hpp:22-23, src/jit.cpp:248-281): stable sort of (key,val) by int key
+int wdb_sort_pairs(int device, void *stream, int32_t *d_keys, float *d_vals, int64_t count, int ascending) {
+  Device *d;
+  if (get_device(device, &d)) return 1;
+  if (count < 0) return fail("negative count");
+  if (count <= 1) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = count;
+  const size_t nb = 4 * (size_t)n;
+  char *buf = nullptr;
+  WDB_CUDA(cudaMallocAsync((void **)&buf, nb * 3, s));
+  unsigned *k = (unsigned *)buf, *kt = (unsigned *)(buf + nb), *pt = (unsigned *)(buf + 2 * nb);
+  const unsigned g = grid_for(d, n);
+  i32_encode_kernel<<<g, 256, 0, s>>>(d_keys, k, n, ascending ? 0 : 1);
+  // the float values ride along as raw 32-bit payloads
+  if (radix_sort<unsigned>(d, s, k, kt, (unsigned *)d_vals, pt, n, 32)) return 1;
+  i32_decode_kernel<<<g, 256, 0, s>>>(k, d_keys, n, ascending ? 0 : 1);
+  stats().launches += 2;
+  WDB_CUDA(cudaGetLastError());
+  WDB_CUDA(cudaFreeAsync(buf, s));
+  return 0;
+}
+}

@@ -410,8 +410,8 @@ static int plan_project(const wdb_col_t *cols, int ncols, const char *expr, cons
   for (const auto &u : p->spec.used)
     if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
   p->variant = (int)opt("project.variant", 0);
-  p->block = (int)opt("project.block", 256);
-  p->unroll = (int)opt("project.unroll", 4);
+  p->block = (int)opt("project.block", 512);   // defaults from profiles/r01_sweep_project_1e9.jsonl
+  p->unroll = (int)opt("project.unroll", 2);
   p->vec = (int)opt("project.vec", 8);
   p->tile = (int)opt("project.tile", 4096);
   p->stages = (int)opt("project.stages", 3);
@@ -430,7 +430,7 @@ static int plan_project(const wdb_col_t *cols, int ncols, const char *expr, cons
   D.push_back({"WDB_VEC", p->vec});
   D.push_back({"WDB_ALIGNED", p->aligned ? 1 : 0});
   D.push_back({"WDB_LD_HINT", opt("project.ld_hint", 0)});
-  D.push_back({"WDB_ST_HINT", opt("project.st_hint", 0)});
+  D.push_back({"WDB_ST_HINT", opt("project.st_hint", p->vec == 8 ? 3 : 0)});
   D.push_back({"WDB_BLOCK", p->block});
   D.push_back({"WDB_UNROLL", p->unroll});
   D.push_back({"WDB_MODE", mode == WDB_DENSE_ZERO ? 2 : 0});
