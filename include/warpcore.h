@@ -93,7 +93,9 @@ int wdb_project_filter(int device, void *stream, const wdb_col_t *cols, int ncol
  * An aggregation table is an opaque per-device object so that chunks (query_multi_gpu_csv) and
  * partial aggregates of other GPUs can be folded into it. */
 typedef struct wdb_agg wdb_agg_t;
-int wdb_agg_create(int device, int64_t expected_groups, wdb_agg_t **out);
+/* needs: which accumulators the table maintains */
+enum { WDB_NEED_SUM = 1, WDB_NEED_COUNT = 2, WDB_NEED_MINMAX = 4, WDB_NEED_FIRST_ROW = 8 };
+int wdb_agg_create(int device, int64_t expected_groups, int needs, wdb_agg_t **out);
 int wdb_agg_destroy(wdb_agg_t *t);
 int wdb_agg_reset(wdb_agg_t *t, void *stream);
 /* fold n rows into the table (cond "" = none).  row_base is the global index of row 0 (first-appearance order). */
@@ -137,9 +139,12 @@ int wdb_column_minmax(int device, void *stream, const wdb_col_t *col, double *h_
 /* ---- multi-GPU: run_multi_gpu_jit_host (include/multi_gpu_utils.hpp:10-12,
  * src/multi_gpu_utils.cpp:5-63).  Host columns in, host floats out; rows are split into
  * contiguous shards chunk = ceil(n/ndev) and all devices run concurrently on their own
- * streams (the reference loops over them sequentially).  h_cols[i].dptr are HOST pointers. */
-int wdb_multi_project_filter_host(int ndev, const wdb_col_t *h_cols, int ncols, const char *expr,
-                                  const char *cond, float *h_out, int64_t n, int mode, int64_t *h_count);
+ * streams (the reference loops over them sequentially).  h_cols[i].dptr are HOST pointers (pinned
+ * memory makes the copies asynchronous).  ndev <= 0: all devices; devices: NULL = 0..ndev-1, else
+ * the device ids to use (one process per GPU passes {its device}). */
+int wdb_multi_project_filter_host(int ndev, const int *devices, const wdb_col_t *h_cols, int ncols,
+                                  const char *expr, const char *cond, float *h_out, int64_t n, int mode,
+                                  int64_t *h_count);
 /* shard [start,end) of device dev: src/multi_gpu_utils.cpp:24-31 */
 int wdb_shard_range(int64_t n, int ndev, int dev, int64_t *start, int64_t *end);
 

@@ -15,6 +15,7 @@ INT32, INT64, FLOAT32, FLOAT64, STRING = 0, 1, 2, 3, 4
 SUM, AVG, COUNT, MIN, MAX = 0, 1, 2, 3, 4
 DENSE, COMPACT, DENSE_ZERO = 0, 1, 2
 ORDER_FIRST, ORDER_KEY_ASC, ORDER_KEY_DESC = 0, 1, 2
+NEED_SUM, NEED_COUNT, NEED_MINMAX, NEED_FIRST_ROW = 1, 2, 4, 8
 
 # every symbol include/warpcore.h declares
 SYMBOLS = [
@@ -61,7 +62,7 @@ def lib():
     L.wdb_get_option.argtypes = [cp, P64]
     L.wdb_get_stats.argtypes = [C.POINTER(Stats)]
     L.wdb_project_filter.argtypes = [ci, vp, PC, ci, cp, cp, vp, i64, ci, vp, P64]
-    L.wdb_agg_create.argtypes = [ci, i64, C.POINTER(vp)]
+    L.wdb_agg_create.argtypes = [ci, i64, ci, C.POINTER(vp)]
     L.wdb_agg_destroy.argtypes = [vp]
     L.wdb_agg_reset.argtypes = [vp, vp]
     L.wdb_agg_consume.argtypes = [vp, vp, PC, ci, cp, cp, cp, i64, i64]
@@ -73,7 +74,7 @@ def lib():
     L.wdb_sort_float.argtypes = [ci, vp, vp, i64, ci]
     L.wdb_sort_pairs.argtypes = [ci, vp, vp, vp, i64, ci]
     L.wdb_column_minmax.argtypes = [ci, vp, PC, C.POINTER(C.c_double), C.POINTER(C.c_double)]
-    L.wdb_multi_project_filter_host.argtypes = [ci, PC, ci, cp, cp, vp, i64, ci, P64]
+    L.wdb_multi_project_filter_host.argtypes = [ci, C.POINTER(ci), PC, ci, cp, cp, vp, i64, ci, P64]
     L.wdb_shard_range.argtypes = [i64, ci, ci, P64, P64]
     L.wdb_synth_f32.argtypes = [ci, vp, vp, i64, C.c_uint64, C.c_float, C.c_float, i64]
     L.wdb_synth_i32.argtypes = [ci, vp, vp, i64, C.c_uint64, C.c_int32, C.c_int32, i64]

@@ -76,6 +76,7 @@ std::string udf_source();
 extern const char *const k_src_prelude;
 extern const char *const k_src_project;
 extern const char *const k_src_compact;
+extern const char *const k_src_group_table;
 extern const char *const k_src_group;
 extern const char *const k_src_topk;
 

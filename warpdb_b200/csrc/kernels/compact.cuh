@@ -16,6 +16,16 @@
 #define WDB_WARP_ROWS (WDB_SLAB_ROWS * WDB_UNROLL)
 #define WDB_TILE_ROWS (WDB_WARP_ROWS * WDB_NWARPS)
 
+// WDB_THRESH: extra keep-test against the run-time threshold wdb_tau on the second expression (the
+// ORDER BY key): 1 keeps key >= tau, 2 keeps key <= tau (negated compares, so NaN keys stay)
+#if WDB_THRESH == 1
+#define WDB_KEEP(R, j) (WDB_COND(R, j) && !(WDB_EXPR2(R, j) < wdb_tau))
+#elif WDB_THRESH == 2
+#define WDB_KEEP(R, j) (WDB_COND(R, j) && !(WDB_EXPR2(R, j) > wdb_tau))
+#else
+#define WDB_KEEP(R, j) WDB_COND(R, j)
+#endif
+
 #define WDB_ST_AGG 1ull
 #define WDB_ST_PREFIX 2ull
 #define WDB_ST_MASK ((1ull << 62) - 1ull)
@@ -36,7 +46,8 @@ __device__ __forceinline__ u64 wdb_warp_sum64(u64 v) {
 
 extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
 wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n,
-            u64 *__restrict__ status, u32 *__restrict__ ticket, i64 *__restrict__ out_count, const i64 ntiles) {
+            u64 *__restrict__ status, u32 *__restrict__ ticket, i64 *__restrict__ out_count, const i64 ntiles,
+            const float wdb_tau, const i64 out_cap) {
   __shared__ float s_stage[WDB_TILE_ROWS];
 #if WDB_NOUT == 2
   __shared__ float s_stage2[WDB_TILE_ROWS];
@@ -68,7 +79,7 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
         u32 m = 0;
 #pragma unroll
         for (int j = 0; j < WDB_VEC; ++j) {
-          m |= (WDB_COND(R[u], j) ? 1u : 0u) << j;
+          m |= (WDB_KEEP(R[u], j) ? 1u : 0u) << j;
           vals[u][j] = WDB_EXPR(R[u], j);
 #if WDB_NOUT == 2
           vals2[u][j] = WDB_EXPR2(R[u], j);
@@ -90,7 +101,7 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
           if (row < n) {
             wdb_rows R;
             wdb_load_row1(C, row, R, 0);
-            if (WDB_COND(R, 0)) {
+            if (WDB_KEEP(R, 0)) {
               m |= 1u << j;
               vals[u][j] = WDB_EXPR(R, 0);
 #if WDB_NOUT == 2
@@ -178,7 +189,7 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
     // copy out with warps writing 128-byte aligned spans of the destination
     const int mis = (int)(g0 & 31);
     for (int i = (int)threadIdx.x - mis; i < (int)ttotal; i += WDB_BLOCK)
-      if (i >= 0) {
+      if (i >= 0 && g0 + i < out_cap) {   // the count stays exact when the output is too small
         out[g0 + i] = s_stage[i];
 #if WDB_NOUT == 2
         out2[g0 + i] = s_stage2[i];

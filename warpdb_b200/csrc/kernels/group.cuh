@@ -1,0 +1,134 @@
+// group.cuh -- fused filter + hash GROUP BY consume kernel (replaces the <<<1,1>>> linear-probe
+// `group_kernel` of src/jit.cpp:192-215 and the std::map loop of src/warpdb.cpp:373-385).
+//
+// key = (int)KEY(row) exactly as `int key = <expr>` (src/jit.cpp:200); accumulators are fp64
+// (src/warpdb.cpp:379-384).  Every CTA pre-aggregates into a private shared-memory hash table
+// (WDB_SMEM_SLOTS slots, native 32-bit CAS on the key, CAS-loop fp64 add -- sm_100 has no native
+// shared fp64 atomic) and folds it into the global open-addressing table once, at the end; rows
+// that do not find a shared slot within WDB_SMEM_PROBES probes go to the global table directly
+// (native RED.ADD.F64 in L2).  With WDB_SMEM_SLOTS == 0 every row goes straight to global memory
+// (large group counts).
+//
+// Roofline: nominally HBM (8 B/row for price,quantity) but in practice bound by the shared-memory
+// atomic rate (small G) or by L2/DRAM random read-modify-write (G >> L2); see DESIGN.md.
+//
+// Host-supplied macros: WDB_BLOCK, WDB_UNROLL, WDB_VEC, WDB_NEEDS, WDB_SMEM_SLOTS (0 or power of
+// two), WDB_SMEM_LOG2, WDB_SMEM_PROBES, WDB_HAS_COND; generated WDB_VAL, WDB_KEY, WDB_COND.
+
+#if WDB_SMEM_SLOTS > 0
+struct wdb_smem_table {
+  int *keys;
+  double *sums;
+  u32 *cnts;
+  i64 *mins;
+  i64 *maxs;
+  i64 *first;
+};
+__device__ __forceinline__ wdb_smem_table wdb_smem_carve(unsigned char *base) {
+  wdb_smem_table S;
+  size_t off = 0;
+  S.sums = reinterpret_cast<double *>(base + off); off += sizeof(double) * WDB_SMEM_SLOTS;
+  S.mins = reinterpret_cast<i64 *>(base + off); off += (WDB_NEEDS & WDB_NEED_MINMAX_BIT) ? sizeof(i64) * WDB_SMEM_SLOTS : 0;
+  S.maxs = reinterpret_cast<i64 *>(base + off); off += (WDB_NEEDS & WDB_NEED_MINMAX_BIT) ? sizeof(i64) * WDB_SMEM_SLOTS : 0;
+  S.first = reinterpret_cast<i64 *>(base + off); off += (WDB_NEEDS & WDB_NEED_FIRST_BIT) ? sizeof(i64) * WDB_SMEM_SLOTS : 0;
+  S.keys = reinterpret_cast<int *>(base + off); off += sizeof(int) * WDB_SMEM_SLOTS;
+  S.cnts = reinterpret_cast<u32 *>(base + off);
+  return S;
+}
+#endif
+
+__device__ __forceinline__ void wdb_group_row(const wdb_table &T,
+#if WDB_SMEM_SLOTS > 0
+                                              const wdb_smem_table &S,
+#endif
+                                              int key, float val, i64 row) {
+  const double dv = (double)val;
+#if WDB_SMEM_SLOTS > 0
+  if (key != WDB_KEY_EMPTY) {
+    u32 h = wdb_hash32(key) >> (32 - WDB_SMEM_LOG2);
+#pragma unroll 1
+    for (int p = 0; p < WDB_SMEM_PROBES; ++p) {
+      const int k = S.keys[h];
+      bool hit = (k == key);
+      if (!hit && k == WDB_KEY_EMPTY) {
+        const int prev = atomicCAS(&S.keys[h], WDB_KEY_EMPTY, key);
+        hit = (prev == WDB_KEY_EMPTY) || (prev == key);
+      }
+      if (hit) {
+        if (WDB_NEEDS & WDB_NEED_SUM_BIT) atomicAdd(&S.sums[h], dv);
+        if (WDB_NEEDS & WDB_NEED_CNT_BIT) atomicAdd(&S.cnts[h], 1u);
+        if (WDB_NEEDS & WDB_NEED_MINMAX_BIT) { const i64 e = wdb_f64_enc(dv); atomicMin(&S.mins[h], e); atomicMax(&S.maxs[h], e); }
+        if (WDB_NEEDS & WDB_NEED_FIRST_BIT) atomicMin(&S.first[h], row);
+        return;
+      }
+      h = (h + 1u) & (WDB_SMEM_SLOTS - 1u);
+    }
+  }
+#endif
+  const i64 s = wdb_table_slot(T, key);
+  if (s >= 0) { const i64 e = wdb_f64_enc(dv); wdb_table_add<WDB_NEEDS>(T, s, dv, 1ull, e, e, row); }
+}
+
+extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
+wdb_group(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T) {
+#if WDB_SMEM_SLOTS > 0
+  extern __shared__ __align__(16) unsigned char wdb_smem[];
+  const wdb_smem_table S = wdb_smem_carve(wdb_smem);
+  for (int s = threadIdx.x; s < WDB_SMEM_SLOTS; s += WDB_BLOCK) {
+    S.keys[s] = WDB_KEY_EMPTY;
+    S.sums[s] = 0.0;
+    S.cnts[s] = 0u;
+    if (WDB_NEEDS & WDB_NEED_MINMAX_BIT) { S.mins[s] = WDB_ENC_PLUS_INF; S.maxs[s] = WDB_ENC_MINUS_INF; }
+    if (WDB_NEEDS & WDB_NEED_FIRST_BIT) S.first[s] = 0x7fffffffffffffffll;
+  }
+  __syncthreads();
+#define WDB_GROUP_ROW(key, val, row) wdb_group_row(T, S, key, val, row)
+#else
+#define WDB_GROUP_ROW(key, val, row) wdb_group_row(T, key, val, row)
+#endif
+  const i64 nvec = n / WDB_VEC;
+  const i64 tile_vecs = (i64)WDB_BLOCK * WDB_UNROLL;
+  const i64 ntiles = (nvec + tile_vecs - 1) / tile_vecs;
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const i64 v0 = tile * tile_vecs + threadIdx.x;
+    wdb_rows R[WDB_UNROLL];
+    const bool full = (tile + 1) * tile_vecs <= nvec;
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u)
+      if (full || v0 + (i64)u * WDB_BLOCK < nvec) wdb_load_rows(C, (v0 + (i64)u * WDB_BLOCK) * WDB_VEC, R[u]);
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) {
+      if (!(full || v0 + (i64)u * WDB_BLOCK < nvec)) continue;
+      const i64 row = (v0 + (i64)u * WDB_BLOCK) * WDB_VEC;
+#pragma unroll
+      for (int j = 0; j < WDB_VEC; ++j) {
+#if WDB_HAS_COND
+        if (!WDB_COND(R[u], j)) continue;
+#endif
+        WDB_GROUP_ROW(WDB_KEY(R[u], j), WDB_VAL(R[u], j), row_base + row + j);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {  // ragged tail
+    const i64 row = nvec * WDB_VEC + threadIdx.x;
+    if (row < n) {
+      wdb_rows R;
+      wdb_load_row1(C, row, R, 0);
+#if WDB_HAS_COND
+      if (WDB_COND(R, 0))
+#endif
+        WDB_GROUP_ROW(WDB_KEY(R, 0), WDB_VAL(R, 0), row_base + row);
+    }
+  }
+#if WDB_SMEM_SLOTS > 0
+  __syncthreads();
+  for (int s = threadIdx.x; s < WDB_SMEM_SLOTS; s += WDB_BLOCK) {
+    const int key = S.keys[s];
+    if (key == WDB_KEY_EMPTY) continue;
+    const i64 g = wdb_table_slot(T, key);
+    if (g >= 0)
+      wdb_table_add<WDB_NEEDS>(T, g, S.sums[s], (u64)S.cnts[s], (WDB_NEEDS & WDB_NEED_MINMAX_BIT) ? S.mins[s] : 0,
+                               (WDB_NEEDS & WDB_NEED_MINMAX_BIT) ? S.maxs[s] : 0, (WDB_NEEDS & WDB_NEED_FIRST_BIT) ? S.first[s] : 0);
+  }
+#endif
+}

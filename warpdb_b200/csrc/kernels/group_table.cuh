@@ -1,0 +1,79 @@
+// group_table.cuh -- device-side open-addressing aggregation table shared by the NVRTC consume
+// kernel (group.cuh) and the statically compiled merge/export kernels (ops_group.cu).
+// Self-contained: compiles under both nvcc and NVRTC.
+//
+// Layout (struct of arrays, capacity cap = mask+1 slots plus one "special" slot at index cap that
+// holds the key equal to the empty-slot sentinel INT_MIN):
+//   keys[cap+1] int32 (INT_MIN = empty)   sums[cap+1] f64   counts[cap+1] u64
+//   mins/maxs[cap+1] order-preserving i64 encodings of f64   first[cap+1] i64 (smallest row id)
+//   meta[0] = groups inserted, meta[1] = overflow flag, meta[2] = special slot used
+#ifndef WDB_GROUP_TABLE_CUH
+#define WDB_GROUP_TABLE_CUH
+
+#define WDB_KEY_EMPTY ((int)0x80000000)
+#define WDB_NEED_SUM_BIT 1
+#define WDB_NEED_CNT_BIT 2
+#define WDB_NEED_MINMAX_BIT 4
+#define WDB_NEED_FIRST_BIT 8
+
+struct wdb_table {
+  int *keys;
+  double *sums;
+  unsigned long long *counts;
+  long long *mins;
+  long long *maxs;
+  long long *first;
+  unsigned int *meta;
+  unsigned int mask;
+};
+
+// monotone map double -> signed 64-bit (a < b  <=>  enc(a) < enc(b) for non-NaN values)
+__device__ __forceinline__ long long wdb_f64_enc(double d) {
+  long long b = __double_as_longlong(d);
+  return b >= 0 ? b : (long long)(0x8000000000000000ull - (unsigned long long)b);
+}
+__device__ __forceinline__ double wdb_f64_dec(long long e) {
+  long long b = e >= 0 ? e : (long long)(0x8000000000000000ull - (unsigned long long)e);
+  return __longlong_as_double(b);
+}
+#define WDB_ENC_PLUS_INF 0x7ff0000000000000ll
+#define WDB_ENC_MINUS_INF (-0x7ff0000000000000ll)
+
+__device__ __forceinline__ unsigned int wdb_hash32(int key) {
+  unsigned int x = (unsigned int)key;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+
+// find or claim the slot of `key`; returns -1 when the table is full (overflow flag raised)
+__device__ __forceinline__ long long wdb_table_slot(const wdb_table &T, int key) {
+  if (key == WDB_KEY_EMPTY) {
+    if (T.meta[2] == 0u) atomicExch(&T.meta[2], 1u);
+    return (long long)T.mask + 1;
+  }
+  unsigned int h = wdb_hash32(key) & T.mask;
+  const unsigned int limit = T.mask < 65535u ? T.mask + 1u : 65536u;
+  for (unsigned int p = 0; p < limit; ++p) {
+    int k = T.keys[h];
+    if (k == key) return h;
+    if (k == WDB_KEY_EMPTY) {
+      const int prev = atomicCAS(&T.keys[h], WDB_KEY_EMPTY, key);
+      if (prev == WDB_KEY_EMPTY) { atomicAdd(&T.meta[0], 1u); return h; }
+      if (prev == key) return h;
+    }
+    h = (h + 1u) & T.mask;
+  }
+  atomicExch(&T.meta[1], 1u);
+  return -1;
+}
+
+// fold one partial aggregate into slot s
+template <int NEEDS>
+__device__ __forceinline__ void wdb_table_add(const wdb_table &T, long long s, double sum, unsigned long long cnt,
+                                              long long mn_enc, long long mx_enc, long long first_row) {
+  if (NEEDS & WDB_NEED_SUM_BIT) atomicAdd(&T.sums[s], sum);
+  if (NEEDS & WDB_NEED_CNT_BIT) atomicAdd(&T.counts[s], cnt);
+  if (NEEDS & WDB_NEED_MINMAX_BIT) { atomicMin(&T.mins[s], mn_enc); atomicMax(&T.maxs[s], mx_enc); }
+  if (NEEDS & WDB_NEED_FIRST_BIT) atomicMin(&T.first[s], first_row);
+}
+#endif

@@ -8,7 +8,7 @@ namespace wdb {
 struct CompactPlan { GenSpec spec; int block, unroll, vec; int64_t tile_rows; bool two; };
 
 static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, const char *expr2, const char *cond,
-                        bool check_alignment, CompactPlan *p) {
+                        bool check_alignment, int thresh, CompactPlan *p) {
   GenSpec &spec = p->spec;
   spec.kind = "compact";
   if (!cond || !*cond) cond = "true";
@@ -17,7 +17,9 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
   spec.used = find_used_columns(cols, ncols, {expr, two ? expr2 : "", cond});
   for (const auto &u : spec.used)
     if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
-  const int block = (int)opt("compact.block", 256), unroll = (int)opt("compact.unroll", 4), vec = (int)opt("compact.vec", 8);
+  const int block = (int)opt("compact.block", 256), vec = (int)opt("compact.vec", 8);
+  int unroll = (int)opt("compact.unroll", 4);
+  while (two && unroll > 1 && (int64_t)block * vec * unroll * 8 > 46 * 1024) unroll /= 2;   // two staging buffers
   if (vec != 4 && vec != 8) return fail("compact.vec must be 4 or 8");
   if (block < 32 || block > 1024 || (block & 31)) return fail("compact.block must be a multiple of 32 in [32,1024]");
   if (unroll < 1 || unroll > 8) return fail("compact.unroll must be in [1,8]");
@@ -26,7 +28,8 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
   if (p->tile_rows * 4 * (two ? 2 : 1) > 46 * 1024) return fail("compact tile of %lld rows does not fit static shared memory", (long long)p->tile_rows);
   const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)vec * 4);
   spec.defines = {{"WDB_VEC", vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("compact.ld_hint", 0)},
-                  {"WDB_ST_HINT", 0}, {"WDB_BLOCK", block}, {"WDB_UNROLL", unroll}, {"WDB_NOUT", two ? 2 : 1}};
+                  {"WDB_ST_HINT", 0}, {"WDB_BLOCK", block}, {"WDB_UNROLL", unroll}, {"WDB_NOUT", two ? 2 : 1},
+                  {"WDB_THRESH", two ? thresh : 0}};
   spec.fns.push_back({"expr", "float", expr});
   if (two) spec.fns.push_back({"expr2", "float", expr2});
   spec.fns.push_back({"cond", "bool", cond});
@@ -37,15 +40,16 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
 int gen_compact_source(const wdb_col_t *cols, int ncols, const char *expr, const char *expr2, const char *cond,
                        bool assume_aligned, std::string *src) {
   CompactPlan p;
-  if (plan_compact(cols, ncols, expr, expr2, cond, !assume_aligned, &p)) return 1;
+  if (plan_compact(cols, ncols, expr, expr2, cond, !assume_aligned, 0, &p)) return 1;
   *src = gen_source(p.spec);
   return 0;
 }
 
-int run_compact(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr, const char *expr2,
-                const char *cond, float *d_out, float *d_out2, int64_t n, int64_t *d_count, int64_t *h_count) {
+int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr, const char *expr2,
+                   const char *cond, float *d_out, float *d_out2, int64_t n, int64_t *d_count, int64_t *h_count,
+                   int thresh, float tau, int64_t out_cap) {
   CompactPlan p;
-  if (plan_compact(cols, ncols, expr, expr2, cond, true, &p)) return 1;
+  if (plan_compact(cols, ncols, expr, expr2, cond, true, thresh, &p)) return 1;
   GenSpec &spec = p.spec;
   const int block = p.block;
   const int64_t tile_rows = p.tile_rows;
@@ -73,7 +77,8 @@ int run_compact(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols
     for (const auto &u : spec.used) ptrs.push_back(cols[u.table_index].dptr);
     if (ptrs.empty()) ptrs.push_back(nullptr);
     long long nn = n, nt = ntiles;
-    void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_ticket, &d_cnt, &nt};
+    long long cap = out_cap;
+    void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_ticket, &d_cnt, &nt, &tau, &cap};
     if (launch(k, grid, block, 0, stream, args)) return 1;
   }
   if (d_count) WDB_CUDA(cudaMemcpyAsync(d_count, d_cnt, 8, cudaMemcpyDeviceToDevice, stream));
@@ -82,6 +87,11 @@ int run_compact(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols
     WDB_CUDA(cudaStreamSynchronize(stream));
   }
   return 0;
+}
+
+int run_compact(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr, const char *expr2,
+                const char *cond, float *d_out, float *d_out2, int64_t n, int64_t *d_count, int64_t *h_count) {
+  return run_compact_ex(d, stream, cols, ncols, expr, expr2, cond, d_out, d_out2, n, d_count, h_count, 0, 0.0f, n);
 }
 
 }  // namespace wdb

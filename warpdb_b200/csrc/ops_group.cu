@@ -1,0 +1,341 @@
+// ops_group.cu -- hash GROUP BY: aggregation-table object, consume launch (kernels/group.cuh via
+// NVRTC), merge of partial aggregates and ordered export.
+//
+// Replaces jit_group_sum (src/jit.cpp:179-246: one thread, O(N*G) linear search, float32 running
+// sums) and the std::map<int,AggData> loop of src/warpdb.cpp:373-437 (fp64 sum/count/min/max, key
+// ascending); jit_sort_pairs on the group arrays (src/warpdb.cpp:370-371) is the ordered export.
+#include <algorithm>
+#include <cstring>
+
+#include "core.hpp"
+#include "kernels/group_table.cuh"
+
+namespace wdb {
+template <class K>
+int radix_sort(Device *d, cudaStream_t s, K *keys, K *tmp_keys, unsigned *pay, unsigned *tmp_pay, long long n, int key_bits);
+}
+
+struct wdb_agg {
+  wdb::Device *dev = nullptr;
+  int needs = 0;
+  int64_t cap = 0;          // power of two
+  char *mem = nullptr;
+  wdb_table T{};
+};
+
+using namespace wdb;
+
+// ---- static kernels ------------------------------------------------------------------------------
+__global__ void agg_init_kernel(wdb_table T, long long slots) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (long long)gridDim.x * blockDim.x) {
+    T.keys[i] = WDB_KEY_EMPTY;
+    T.sums[i] = 0.0;
+    T.counts[i] = 0ull;
+    T.mins[i] = WDB_ENC_PLUS_INF;
+    T.maxs[i] = WDB_ENC_MINUS_INF;
+    T.first[i] = 0x7fffffffffffffffll;
+    if (i < 4) T.meta[i] = 0u;
+  }
+}
+
+template <int NEEDS>
+__global__ void agg_merge_kernel(wdb_table T, const int *__restrict__ keys, const double *__restrict__ sums,
+                                 const long long *__restrict__ counts, const double *__restrict__ mins,
+                                 const double *__restrict__ maxs, const long long *__restrict__ first, long long m) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = wdb_table_slot(T, keys[i]);
+    if (s < 0) continue;
+    wdb_table_add<NEEDS>(T, s, (NEEDS & WDB_NEED_SUM_BIT) ? sums[i] : 0.0, (NEEDS & WDB_NEED_CNT_BIT) ? (unsigned long long)counts[i] : 0ull,
+                         (NEEDS & WDB_NEED_MINMAX_BIT) ? wdb_f64_enc(mins[i]) : 0, (NEEDS & WDB_NEED_MINMAX_BIT) ? wdb_f64_enc(maxs[i]) : 0,
+                         (NEEDS & WDB_NEED_FIRST_BIT) ? first[i] : 0);
+  }
+}
+
+// occupied slots -> (sort key, slot) pairs.  order: 0 first appearance, 1 key asc, 2 key desc
+__global__ void agg_collect_kernel(wdb_table T, long long slots, int order, unsigned long long *__restrict__ sort_keys,
+                                   unsigned *__restrict__ sort_slots, unsigned long long *__restrict__ counter) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (long long)gridDim.x * blockDim.x) {
+    const bool special = i == slots - 1;
+    const bool used = special ? (T.meta[2] != 0u) : (T.keys[i] != WDB_KEY_EMPTY);
+    if (!used) continue;
+    const int key = special ? WDB_KEY_EMPTY : T.keys[i];
+    unsigned long long k;
+    if (order == 0) k = (unsigned long long)T.first[i];
+    else {
+      k = (unsigned long long)((unsigned)key ^ 0x80000000u);
+      if (order == 2) k = 0xffffffffull - k;
+    }
+    const unsigned long long pos = atomicAdd(counter, 1ull);
+    sort_keys[pos] = k;
+    sort_slots[pos] = (unsigned)i;
+  }
+}
+
+__global__ void agg_emit_kernel(wdb_table T, long long slots, const unsigned *__restrict__ sorted_slots, long long g, int agg,
+                                int *__restrict__ o_keys, float *__restrict__ o_vals, double *__restrict__ o_sums,
+                                long long *__restrict__ o_counts, double *__restrict__ o_mins, double *__restrict__ o_maxs,
+                                long long *__restrict__ o_first) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned s = sorted_slots[i];
+    const int key = (s == slots - 1) ? WDB_KEY_EMPTY : T.keys[s];
+    const double sum = T.sums[s];
+    const double cnt = (double)T.counts[s];
+    const double mn = wdb_f64_dec(T.mins[s]), mx = wdb_f64_dec(T.maxs[s]);
+    if (o_keys) o_keys[i] = key;
+    if (o_vals) {  // src/warpdb.cpp:429-435: double results narrowed to float
+      float v;
+      switch (agg) {
+      case WDB_SUM: v = (float)sum; break;
+      case WDB_AVG: v = (float)(sum / cnt); break;
+      case WDB_COUNT: v = (float)cnt; break;
+      case WDB_MIN: v = (float)mn; break;
+      default: v = (float)mx; break;
+      }
+      o_vals[i] = v;
+    }
+    if (o_sums) o_sums[i] = sum;
+    if (o_counts) o_counts[i] = (long long)T.counts[s];
+    if (o_mins) o_mins[i] = mn;
+    if (o_maxs) o_maxs[i] = mx;
+    if (o_first) o_first[i] = T.first[s];
+  }
+}
+
+namespace wdb {
+
+static int needs_for_agg(int agg) {
+  switch (agg) {
+  case WDB_SUM: return WDB_NEED_SUM_BIT;
+  case WDB_AVG: return WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT;
+  case WDB_COUNT: return WDB_NEED_CNT_BIT;
+  case WDB_MIN: case WDB_MAX: return WDB_NEED_MINMAX_BIT;
+  }
+  return 0;
+}
+
+static unsigned grid_for(Device *d, long long n) {
+  return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)d->num_sms * 16));
+}
+
+struct GroupPlan { GenSpec spec; int block, unroll, vec, smem_slots; size_t smem_bytes; };
+
+static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const char *key, const char *cond, int needs,
+                      int64_t cap_hint, bool check_alignment, GroupPlan *p) {
+  const bool has_cond = cond && *cond;
+  GenSpec &spec = p->spec;
+  spec.kind = "group";
+  spec.used = find_used_columns(cols, ncols, {val, key, has_cond ? cond : ""});
+  for (const auto &u : spec.used)
+    if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
+  p->block = (int)opt("group.block", 256);
+  p->unroll = (int)opt("group.unroll", 2);
+  p->vec = (int)opt("group.vec", 4);
+  if (p->vec != 4 && p->vec != 8) return fail("group.vec must be 4 or 8");
+  // shared pre-aggregation pays when the distinct keys fit the shared table; beyond that every row
+  // misses it and the probes are wasted work
+  int64_t slots = opt("group.smem_slots", -1);
+  if (slots < 0) slots = (cap_hint / 2 <= 2048) ? 4096 : 0;   // cap_hint = table capacity = 2 x expected groups
+  if (slots & (slots - 1)) return fail("group.smem_slots must be a power of two");
+  p->smem_slots = (int)slots;
+  int log2 = 0;
+  while ((1ll << log2) < slots) ++log2;
+  size_t per_slot = 8 + 4 + 4 + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) + ((needs & WDB_NEED_FIRST_BIT) ? 8 : 0);
+  p->smem_bytes = per_slot * (size_t)slots;
+  const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)p->vec * 4);
+  spec.defines = {{"WDB_VEC", p->vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("group.ld_hint", 0)}, {"WDB_ST_HINT", 0},
+                  {"WDB_BLOCK", p->block}, {"WDB_UNROLL", p->unroll}, {"WDB_NEEDS", needs}, {"WDB_SMEM_SLOTS", slots},
+                  {"WDB_SMEM_LOG2", log2}, {"WDB_SMEM_PROBES", opt("group.smem_probes", 4)}, {"WDB_HAS_COND", has_cond ? 1 : 0}};
+  spec.fns.push_back({"val", "float", (needs & ~WDB_NEED_CNT_BIT & ~WDB_NEED_FIRST_BIT) ? val : "0.0f"});  // COUNT never evaluates its argument (src/warpdb.cpp:376)
+  spec.fns.push_back({"key", "int", key});
+  if (has_cond) spec.fns.push_back({"cond", "bool", cond});
+  spec.bodies = {k_src_group_table, k_src_group};
+  return 0;
+}
+
+int gen_group_source(const wdb_col_t *cols, int ncols, const char *val, const char *key, const char *cond, int agg,
+                     std::string *src) {
+  GroupPlan p;
+  if (plan_group(cols, ncols, val, key, cond, needs_for_agg(agg), 2048, false, &p)) return 1;
+  *src = gen_source(p.spec);
+  return 0;
+}
+
+}  // namespace wdb
+
+extern "C" {
+
+int wdb_agg_create(int device, int64_t expected_groups, int needs, wdb_agg_t **out) {
+  Device *d;
+  if (get_device(device, &d)) return 1;
+  if (!out) return fail("null output");
+  if (needs <= 0 || needs > 15) return fail("invalid needs mask %d", needs);
+  int64_t want = std::max<int64_t>(expected_groups, 512) * 2, cap = 1024;
+  while (cap < want) cap <<= 1;
+  if (cap > (1ll << 31)) return fail("aggregation table of %lld slots is too large", (long long)cap);
+  wdb_agg *t = new wdb_agg();
+  t->dev = d;
+  t->needs = needs;
+  t->cap = cap;
+  const size_t slots = (size_t)cap + 1;
+  const size_t bytes = slots * (4 + 8 + 8 + 8 + 8 + 8) + 256 + 64;
+  cudaError_t e = cudaMalloc((void **)&t->mem, bytes);
+  if (e != cudaSuccess) { delete t; return fail("CUDA error: %s (aggregation table of %zu bytes)", cudaGetErrorString(e), bytes); }
+  char *p = t->mem;
+  t->T.sums = (double *)p; p += 8 * slots;
+  t->T.counts = (unsigned long long *)p; p += 8 * slots;
+  t->T.mins = (long long *)p; p += 8 * slots;
+  t->T.maxs = (long long *)p; p += 8 * slots;
+  t->T.first = (long long *)p; p += 8 * slots;
+  t->T.keys = (int *)p; p += 4 * slots;
+  p = (char *)(((uintptr_t)p + 63) & ~(uintptr_t)63);
+  t->T.meta = (unsigned *)p;
+  t->T.mask = (unsigned)(cap - 1);
+  if (wdb_agg_reset(t, nullptr)) { cudaFree(t->mem); delete t; return 1; }
+  *out = t;
+  return 0;
+}
+
+int wdb_agg_destroy(wdb_agg_t *t) {
+  if (!t) return 0;
+  cudaSetDevice(t->dev->id);
+  cudaFree(t->mem);
+  delete t;
+  return 0;
+}
+
+int wdb_agg_reset(wdb_agg_t *t, void *stream) {
+  if (!t) return fail("null table");
+  WDB_CUDA(cudaSetDevice(t->dev->id));
+  agg_init_kernel<<<grid_for(t->dev, t->cap + 1), 256, 0, (cudaStream_t)stream>>>(t->T, t->cap + 1);
+  stats().launches++;
+  WDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols, const char *val_expr, const char *key_expr,
+                    const char *cond, int64_t n, int64_t row_base) {
+  if (!t) return fail("null table");
+  if (!key_expr || !*key_expr) return fail("empty GROUP BY key expression");
+  if (!val_expr || !*val_expr) val_expr = "0.0f";
+  if (n < 0) return fail("negative row count");
+  Device *d = t->dev;
+  WDB_CUDA(cudaSetDevice(d->id));
+  GroupPlan p;
+  if (plan_group(cols, ncols, val_expr, key_expr, cond, t->needs, t->cap, true, &p)) return 1;
+  Kernel k;
+  if (get_kernel(d, gen_source(p.spec), "wdb_group.cu", "wdb_group", &k)) return 1;
+  if (n == 0) return 0;
+  if (p.smem_bytes > 48 * 1024) WDB_CUDA(cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+  int nb = 0;
+  WDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)k.fn, p.block, p.smem_bytes));
+  nb = std::max(1, std::min<int>(nb, (int)opt("group.ctas_per_sm", 8)));
+  const int64_t tile_rows = (int64_t)p.block * p.unroll * p.vec;
+  const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
+  unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)d->num_sms * nb));
+  std::vector<const void *> ptrs;
+  for (const auto &u : p.spec.used) ptrs.push_back(cols[u.table_index].dptr);
+  if (ptrs.empty()) ptrs.push_back(nullptr);
+  long long nn = n, rb = row_base;
+  void *args[] = {ptrs.data(), &nn, &rb, &t->T};
+  return launch(k, grid, p.block, p.smem_bytes, (cudaStream_t)stream, args);
+}
+
+int wdb_agg_merge(wdb_agg_t *t, void *stream, const int32_t *d_keys, const double *d_sums, const int64_t *d_counts,
+                  const double *d_mins, const double *d_maxs, const int64_t *d_first, int64_t m) {
+  if (!t) return fail("null table");
+  if (m <= 0) return 0;
+  const int needs = t->needs;
+  if (!d_keys) return fail("merge needs the partial keys");
+  if ((needs & WDB_NEED_SUM_BIT) && !d_sums) return fail("merge needs the partial sums");
+  if ((needs & WDB_NEED_CNT_BIT) && !d_counts) return fail("merge needs the partial counts");
+  if ((needs & WDB_NEED_MINMAX_BIT) && (!d_mins || !d_maxs)) return fail("merge needs the partial minima and maxima");
+  if ((needs & WDB_NEED_FIRST_BIT) && !d_first) return fail("merge needs the partial first rows");
+  WDB_CUDA(cudaSetDevice(t->dev->id));
+  const unsigned g = grid_for(t->dev, m);
+  cudaStream_t s = (cudaStream_t)stream;
+#define WDB_MERGE_CASE(N) case N: agg_merge_kernel<N><<<g, 256, 0, s>>>(t->T, d_keys, d_sums, (const long long *)d_counts, d_mins, d_maxs, (const long long *)d_first, m); break;
+  switch (needs) {
+    WDB_MERGE_CASE(1) WDB_MERGE_CASE(2) WDB_MERGE_CASE(3) WDB_MERGE_CASE(4) WDB_MERGE_CASE(5) WDB_MERGE_CASE(6) WDB_MERGE_CASE(7)
+    WDB_MERGE_CASE(8) WDB_MERGE_CASE(9) WDB_MERGE_CASE(10) WDB_MERGE_CASE(11) WDB_MERGE_CASE(12) WDB_MERGE_CASE(13) WDB_MERGE_CASE(14) WDB_MERGE_CASE(15)
+  }
+#undef WDB_MERGE_CASE
+  stats().launches++;
+  WDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int read_meta(wdb_agg_t *t, cudaStream_t s, unsigned meta[4]) {
+  WDB_CUDA(cudaMemcpyAsync(meta, t->T.meta, 16, cudaMemcpyDeviceToHost, s));
+  WDB_CUDA(cudaStreamSynchronize(s));
+  if (meta[1]) return fail("aggregation table overflow: more than %lld distinct keys; recreate it with a larger expected_groups", (long long)(t->cap / 2));
+  return 0;
+}
+
+int wdb_agg_size(wdb_agg_t *t, void *stream, int64_t *h_groups) {
+  if (!t) return fail("null table");
+  WDB_CUDA(cudaSetDevice(t->dev->id));
+  unsigned meta[4];
+  if (read_meta(t, (cudaStream_t)stream, meta)) return 1;
+  *h_groups = (int64_t)meta[0] + (meta[2] ? 1 : 0);
+  return 0;
+}
+
+int wdb_agg_export(wdb_agg_t *t, void *stream, int agg, int order, int32_t *d_keys, float *d_vals, double *d_sums,
+                   int64_t *d_counts, double *d_mins, double *d_maxs, int64_t *d_first, int64_t cap, int64_t *h_groups) {
+  if (!t) return fail("null table");
+  if (agg < WDB_SUM || agg > WDB_MAX) return fail("invalid aggregation %d", agg);
+  if (order < 0 || order > 2) return fail("invalid order %d", order);
+  if (d_vals && (needs_for_agg(agg) & ~t->needs)) return fail("the table does not track what aggregation %d needs", agg);
+  if (order == WDB_ORDER_FIRST && !(t->needs & WDB_NEED_FIRST_BIT)) return fail("first-appearance order needs a table created with the first-row bit");
+  Device *d = t->dev;
+  WDB_CUDA(cudaSetDevice(d->id));
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned meta[4];
+  if (read_meta(t, s, meta)) return 1;
+  const long long g = (long long)meta[0] + (meta[2] ? 1 : 0);
+  if (h_groups) *h_groups = g;
+  if (g == 0) return 0;
+  if (g > cap) return fail("%lld groups exceed the output capacity %lld", g, (long long)cap);
+  const long long slots = t->cap + 1;
+  char *buf = nullptr;
+  const size_t kb = 8 * (size_t)g, pb = 4 * (size_t)g;
+  WDB_CUDA(cudaMallocAsync((void **)&buf, 2 * kb + 2 * pb + 64, s));
+  unsigned long long *sk = (unsigned long long *)buf, *skt = (unsigned long long *)(buf + kb);
+  unsigned *sp = (unsigned *)(buf + 2 * kb), *spt = (unsigned *)(buf + 2 * kb + pb);
+  unsigned long long *counter = (unsigned long long *)(buf + 2 * kb + 2 * pb);
+  WDB_CUDA(cudaMemsetAsync(counter, 0, 8, s));
+  agg_collect_kernel<<<grid_for(d, slots), 256, 0, s>>>(t->T, slots, order, sk, sp, counter);
+  // collection order is arbitrary (atomic counter); sorting on the full key makes the export
+  // deterministic: group keys are unique, first-appearance rows are unique
+  if (radix_sort<unsigned long long>(d, s, sk, skt, sp, spt, g, order == WDB_ORDER_FIRST ? 64 : 32)) return 1;
+  agg_emit_kernel<<<grid_for(d, g), 256, 0, s>>>(t->T, slots, sp, g, agg, d_keys, d_vals, d_sums, (long long *)d_counts, d_mins, d_maxs,
+                                                  (long long *)d_first);
+  stats().launches += 2;
+  WDB_CUDA(cudaGetLastError());
+  WDB_CUDA(cudaFreeAsync(buf, s));
+  WDB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int wdb_group_agg(int device, void *stream, const wdb_col_t *cols, int ncols, const char *val_expr, const char *key_expr,
+                  const char *cond, int agg, int order, int64_t n, int64_t expected_groups, int32_t *d_keys, float *d_vals,
+                  int64_t cap, int64_t *h_groups) {
+  if (agg < WDB_SUM || agg > WDB_MAX) return fail("invalid aggregation %d", agg);
+  int needs = needs_for_agg(agg) | (order == WDB_ORDER_FIRST ? WDB_NEED_FIRST_BIT : 0);
+  int64_t expect = expected_groups > 0 ? expected_groups : 1 << 16;
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    wdb_agg_t *t = nullptr;
+    if (wdb_agg_create(device, expect, needs, &t)) return 1;
+    int rc = wdb_agg_consume(t, stream, cols, ncols, val_expr, key_expr, cond, n, 0);
+    int64_t g = 0;
+    if (!rc) rc = wdb_agg_export(t, stream, agg, order, d_keys, d_vals, nullptr, nullptr, nullptr, nullptr, nullptr, cap, &g);
+    const bool overflow = rc && strstr(wdb_last_error(), "table overflow") != nullptr;
+    wdb_agg_destroy(t);
+    if (!rc) { if (h_groups) *h_groups = g; return 0; }
+    if (!overflow) return 1;
+    expect *= 16;  // unknown cardinality: grow and run again
+    if (expect > (1ll << 30)) break;
+  }
+  return fail("aggregation table overflow: too many distinct keys");
+}
+}

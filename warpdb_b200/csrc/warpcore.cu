@@ -447,7 +447,7 @@ static int plan_project(const wdb_col_t *cols, int ncols, const char *expr, cons
   return 0;
 }
 
-static int run_project(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr,
+int run_project(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr,
                        const char *cond, float *d_out, int64_t n, int mode) {
   ProjectPlan p;
   if (plan_project(cols, ncols, expr, cond, d_out, mode, &p, true)) return 1;
@@ -480,6 +480,8 @@ static int run_project(Device *d, cudaStream_t stream, const wdb_col_t *cols, in
 // source a call of the given kind would compile (no device needed): used by wdb_debug_compile
 int gen_compact_source(const wdb_col_t *cols, int ncols, const char *expr, const char *expr2, const char *cond,
                        bool assume_aligned, std::string *src);
+int gen_group_source(const wdb_col_t *cols, int ncols, const char *val, const char *key, const char *cond, int agg, std::string *src);
+int gen_topk_source(const wdb_col_t *cols, int ncols, const char *key, const char *val, const char *cond, int desc, std::string *src);
 int gen_kernel_source(const std::string &kind, const wdb_col_t *cols, int ncols, const char *a, const char *b,
                       const char *cond, int mode, std::string *src, std::string *name) {
   if (!a || !*a) return fail("empty expression");
@@ -493,6 +495,14 @@ int gen_kernel_source(const std::string &kind, const wdb_col_t *cols, int ncols,
   if (kind == "compact") {
     *name = "wdb_compact.cu";
     return gen_compact_source(cols, ncols, a, b, cond, true, src);
+  }
+  if (kind == "group") {
+    *name = "wdb_group.cu";
+    return gen_group_source(cols, ncols, a, b, cond, mode, src);   // mode = aggregation type
+  }
+  if (kind == "topk") {
+    *name = "wdb_topk.cu";
+    return gen_topk_source(cols, ncols, a, b, cond, mode, src);    // mode = descending
   }
   return fail("wdb_debug_compile: unknown kernel kind '%s'", kind.c_str());
 }

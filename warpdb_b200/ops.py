@@ -66,3 +66,129 @@ def synth_i32(n, seed, lo, hi_excl, row0=0, device=0):
     out = torch.empty(n, dtype=torch.int32, device=f"cuda:{device}")
     wc.check(wc.lib().wdb_synth_i32(device, _stream(device), out.data_ptr(), n, seed, lo, hi_excl, row0))
     return out
+
+
+class AggTable:
+    """Device-resident hash aggregation table (wdb_agg_*): fold row chunks and partial aggregates of
+    other GPUs into it, then export ordered groups."""
+
+    def __init__(self, device=0, expected_groups=1 << 16, needs=wc.NEED_SUM | wc.NEED_COUNT):
+        self.device = device
+        self.needs = needs
+        self.handle = C.c_void_p()
+        wc.check(wc.lib().wdb_agg_create(device, expected_groups, needs, C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            wc.lib().wdb_agg_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def reset(self):
+        wc.check(wc.lib().wdb_agg_reset(self.handle, _stream(self.device)))
+
+    def consume(self, table, val_expr, key_expr, cond=None, n=None, row_base=0):
+        n = num_rows(table) if n is None else n
+        cols, nc = wc.make_cols(schema_of(table))
+        wc.check(wc.lib().wdb_agg_consume(self.handle, _stream(self.device), cols, nc, wc.enc(val_expr), wc.enc(key_expr),
+                                          wc.enc(cond or ""), n, row_base))
+
+    def merge(self, part):
+        """part: dict with keys (int32) and whichever of sums/counts/mins/maxs/first the table tracks."""
+        def p(name):
+            t = part.get(name)
+            return t.data_ptr() if t is not None and t.numel() else None
+        m = part["keys"].numel()
+        wc.check(wc.lib().wdb_agg_merge(self.handle, _stream(self.device), p("keys"), p("sums"), p("counts"), p("mins"),
+                                        p("maxs"), p("first"), m))
+
+    def size(self):
+        g = C.c_int64(0)
+        wc.check(wc.lib().wdb_agg_size(self.handle, _stream(self.device), C.byref(g)))
+        return g.value
+
+    def export(self, agg=wc.SUM, order=wc.ORDER_KEY_ASC, raw=True):
+        """Returns dict(keys, vals[, sums, counts, mins, maxs, first]) of CUDA tensors."""
+        g = self.size()
+        dev = f"cuda:{self.device}"
+        out = {"keys": torch.empty(g, dtype=torch.int32, device=dev)}
+        have_val = {wc.SUM: wc.NEED_SUM, wc.AVG: wc.NEED_SUM | wc.NEED_COUNT, wc.COUNT: wc.NEED_COUNT,
+                    wc.MIN: wc.NEED_MINMAX, wc.MAX: wc.NEED_MINMAX}[agg]
+        if (have_val & ~self.needs) == 0:
+            out["vals"] = torch.empty(g, dtype=torch.float32, device=dev)
+        if raw:
+            if self.needs & wc.NEED_SUM:
+                out["sums"] = torch.empty(g, dtype=torch.float64, device=dev)
+            if self.needs & wc.NEED_COUNT:
+                out["counts"] = torch.empty(g, dtype=torch.int64, device=dev)
+            if self.needs & wc.NEED_MINMAX:
+                out["mins"] = torch.empty(g, dtype=torch.float64, device=dev)
+                out["maxs"] = torch.empty(g, dtype=torch.float64, device=dev)
+            if self.needs & wc.NEED_FIRST_ROW:
+                out["first"] = torch.empty(g, dtype=torch.int64, device=dev)
+
+        def p(name):
+            t = out.get(name)
+            return t.data_ptr() if t is not None and t.numel() else None
+        gg = C.c_int64(0)
+        wc.check(wc.lib().wdb_agg_export(self.handle, _stream(self.device), agg, order, p("keys"), p("vals"), p("sums"),
+                                         p("counts"), p("mins"), p("maxs"), p("first"), g, C.byref(gg)))
+        assert gg.value == g
+        return out
+
+
+def needs_for(agg, order=wc.ORDER_KEY_ASC):
+    n = {wc.SUM: wc.NEED_SUM, wc.AVG: wc.NEED_SUM | wc.NEED_COUNT, wc.COUNT: wc.NEED_COUNT, wc.MIN: wc.NEED_MINMAX,
+         wc.MAX: wc.NEED_MINMAX}[agg]
+    return n | (wc.NEED_FIRST_ROW if order == wc.ORDER_FIRST else 0)
+
+
+def group_agg(table, val_expr, key_expr, cond=None, agg=wc.SUM, order=wc.ORDER_KEY_ASC, expected_groups=0, cap=None):
+    """One-shot GROUP BY: returns (keys int32[G], vals float32[G])."""
+    dev = _dev_index(table)
+    n = num_rows(table)
+    cap = cap if cap is not None else max(min(n, 1 << 26), 1)
+    if expected_groups:
+        cap = max(min(cap, 2 * expected_groups + 16), 1)
+    keys = torch.empty(cap, dtype=torch.int32, device=f"cuda:{dev}")
+    vals = torch.empty(cap, dtype=torch.float32, device=f"cuda:{dev}")
+    cols, nc = wc.make_cols(schema_of(table))
+    g = C.c_int64(0)
+    wc.check(wc.lib().wdb_group_agg(dev, _stream(dev), cols, nc, wc.enc(val_expr), wc.enc(key_expr), wc.enc(cond or ""), agg,
+                                    order, n, expected_groups, keys.data_ptr(), vals.data_ptr(), cap, C.byref(g)))
+    return keys[:g.value], vals[:g.value]
+
+
+def topk(table, key_expr, val_expr=None, cond=None, descending=True, k=5, offset=0, want_keys=False):
+    """ORDER BY key_expr [LIMIT k [OFFSET offset]] (k < 0: no limit).  Returns vals (and keys)."""
+    dev = _dev_index(table)
+    n = num_rows(table)
+    m = n if k < 0 else min(k, n)
+    vals = torch.empty(max(m, 1), dtype=torch.float32, device=f"cuda:{dev}")
+    keys = torch.empty(max(m, 1), dtype=torch.float32, device=f"cuda:{dev}")
+    cols, nc = wc.make_cols(schema_of(table))
+    cnt = C.c_int64(0)
+    wc.check(wc.lib().wdb_topk(dev, _stream(dev), cols, nc, wc.enc(key_expr), wc.enc(val_expr), wc.enc(cond or ""),
+                               int(descending), k, offset, n, vals.data_ptr(), keys.data_ptr(), C.byref(cnt)))
+    if want_keys:
+        return vals[:cnt.value], keys[:cnt.value]
+    return vals[:cnt.value]
+
+
+def sort_float(vals, ascending=True):
+    """In-place stable device sort (jit_sort_float)."""
+    dev = vals.device.index or 0
+    wc.check(wc.lib().wdb_sort_float(dev, _stream(dev), vals.data_ptr(), vals.numel(), int(ascending)))
+    return vals
+
+
+def sort_pairs(keys, vals, ascending=True):
+    """In-place stable device sort of (int32 key, float32 value) pairs by key (jit_sort_pairs)."""
+    dev = keys.device.index or 0
+    wc.check(wc.lib().wdb_sort_pairs(dev, _stream(dev), keys.data_ptr(), vals.data_ptr(), keys.numel(), int(ascending)))
+    return keys, vals
