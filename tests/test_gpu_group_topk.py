@@ -84,7 +84,7 @@ def test_table_overflow_is_reported_and_retried():
     with pytest.raises(wc.WarpcoreError, match="table overflow"):
         tab.size()
     tab.close()
-    k, v = ops.group_agg(dev(t), "price[idx]", "quantity[idx]", expected_groups=1000)   # grows and reruns
+    k, v = ops.group_agg(dev(t), "price[idx]", "quantity[idx]", expected_groups=1000, cap=n)   # grows and reruns
     assert np.array_equal(k.cpu().numpy(), t["quantity"]) and np.array_equal(bits(v.cpu().numpy()), bits(t["price"]))
 
 

@@ -122,10 +122,12 @@ def sweep_compact(n):
         rec = {"name": "torch masked_select", "sel": cnt / n, "ms": ms, "gbs": gb / (ms * 1e-3)}
         print(json.dumps(rec), flush=True)
         f.write(json.dumps(rec) + "\n")
-        for vec, unroll, block, ctas in itertools.product([4, 8], [1, 2, 4], [256, 512], [4, 8]):
-            if block * vec * unroll * 4 > 46 * 1024:
+        for vec, unroll, block, minc, lb in itertools.product([4, 8], [1, 2, 4], [256, 512], [1, 2, 3, 4], [1, 4]):
+            if block * vec * unroll * 4 > 46 * 1024 or minc * block > 1024 * 2:
                 continue
-            cfg = {"vec": vec, "unroll": unroll, "block": block, "ctas_per_sm": ctas}
+            if lb == 1 and not (vec == 8 and unroll == 4):
+                continue
+            cfg = {"vec": vec, "unroll": unroll, "block": block, "min_ctas": minc, "lookback": lb, "ctas_per_sm": 8}
             for k, v in cfg.items():
                 wc.set_option("compact." + k, v)
             try:

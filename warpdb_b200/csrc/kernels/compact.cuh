@@ -44,7 +44,44 @@ __device__ __forceinline__ u64 wdb_warp_sum64(u64 v) {
   return v;
 }
 
-extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
+// Decoupled look-back over a window of 32*WDB_LB predecessor tiles per step: lane l inspects the
+// WDB_LB status words of tiles look-(l*WDB_LB+q).  Returns the exclusive prefix of `tile`.
+#ifndef WDB_LB
+#define WDB_LB 4
+#endif
+__device__ __forceinline__ i64 wdb_lookback(const u64 *__restrict__ status, const i64 tile, const u32 lane) {
+  i64 excl = 0;
+  i64 look = tile - 1;
+  while (true) {
+    u64 part = 0;          // sum of this lane's statuses up to and including its first PREFIX
+    bool has_prefix = false;
+#pragma unroll
+    for (int q = 0; q < WDB_LB; ++q) {
+      const i64 idx = look - ((i64)lane * WDB_LB + q);
+      u64 st = (WDB_ST_PREFIX << 62);              // tiles before the first one: prefix 0
+      if (idx >= 0) {
+        do { st = wdb_ld_status(&status[idx]); } while ((st >> 62) == 0ull);
+      }
+      if (!has_prefix) {
+        part += st & WDB_ST_MASK;
+        has_prefix = (st >> 62) == WDB_ST_PREFIX;
+      }
+    }
+    const u32 pm = __ballot_sync(WDB_FULL_MASK, has_prefix);
+    if (pm) {
+      const u32 first = (u32)__ffs((int)pm) - 1u;
+      excl += (i64)wdb_warp_sum64(lane <= first ? part : 0ull);
+      return excl;
+    }
+    excl += (i64)wdb_warp_sum64(part);
+    look -= 32 * WDB_LB;
+  }
+}
+
+#ifndef WDB_MIN_CTAS
+#define WDB_MIN_CTAS 1
+#endif
+extern "C" __global__ void __launch_bounds__(WDB_BLOCK, WDB_MIN_CTAS)
 wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n,
             u64 *__restrict__ status, u32 *__restrict__ ticket, i64 *__restrict__ out_count, const i64 ntiles,
             const float wdb_tau, const i64 out_cap) {
@@ -54,15 +91,26 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
 #endif
   __shared__ u32 s_wcount[WDB_NWARPS];
   __shared__ i64 s_base;
-  __shared__ u32 s_tile;
+  __shared__ u32 s_tile[2];
   const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const u32 lt = wdb_lanemask_lt();
 
-  while (true) {
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();                                            // (1)
-    const i64 tile = (i64)s_tile;
-    if (tile >= ntiles) break;
+  // Tiles are handed out in ticket order, so every predecessor of a tile is owned by a CTA that is
+  // already running: the look-back can never wait on work that has not been scheduled.
+  if (threadIdx.x == 0) s_tile[0] = atomicAdd(ticket, 1u);
+  __syncthreads();
+  i64 tile = (i64)s_tile[0];
+  wdb_rows R[WDB_UNROLL];
+  bool full = tile < ntiles && (tile + 1) * WDB_TILE_ROWS <= n;
+  if (full) {
+    const i64 r0 = tile * WDB_TILE_ROWS + (i64)warp * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows(C, r0 + (i64)u * WDB_SLAB_ROWS, R[u]);
+  }
+
+  for (u32 it = 0; tile < ntiles; ++it) {
+    // the next ticket is requested now and read after the barrier below: its latency is hidden
+    if (threadIdx.x == 0) s_tile[(it + 1u) & 1u] = atomicAdd(ticket, 1u);
     const i64 wrow0 = tile * WDB_TILE_ROWS + (i64)warp * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
 
     u32 flags[WDB_UNROLL];
@@ -70,10 +118,7 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
 #if WDB_NOUT == 2
     float vals2[WDB_UNROLL][WDB_VEC];
 #endif
-    if ((tile + 1) * WDB_TILE_ROWS <= n) {
-      wdb_rows R[WDB_UNROLL];
-#pragma unroll
-      for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows(C, wrow0 + (i64)u * WDB_SLAB_ROWS, R[u]);
+    if (full) {
 #pragma unroll
       for (int u = 0; u < WDB_UNROLL; ++u) {
         u32 m = 0;
@@ -87,7 +132,7 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
         }
         flags[u] = m;
       }
-    } else {
+    } else {  // ragged last tile
 #pragma unroll
       for (int u = 0; u < WDB_UNROLL; ++u) {
         u32 m = 0;
@@ -99,13 +144,13 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
           vals2[u][j] = 0.0f;
 #endif
           if (row < n) {
-            wdb_rows R;
-            wdb_load_row1(C, row, R, 0);
-            if (WDB_KEEP(R, 0)) {
+            wdb_rows T1;
+            wdb_load_row1(C, row, T1, 0);
+            if (WDB_KEEP(T1, 0)) {
               m |= 1u << j;
-              vals[u][j] = WDB_EXPR(R, 0);
+              vals[u][j] = WDB_EXPR(T1, 0);
 #if WDB_NOUT == 2
-              vals2[u][j] = WDB_EXPR2(R, 0);
+              vals2[u][j] = WDB_EXPR2(T1, 0);
 #endif
             }
           }
@@ -130,7 +175,8 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
       wtotal += tot;
     }
     if (lane == 0) s_wcount[warp] = wtotal;
-    __syncthreads();                                            // (2)
+    __syncthreads();                                            // (A)
+    const i64 next_tile = (i64)s_tile[(it + 1u) & 1u];
     u32 woff = 0, ttotal = 0;
 #pragma unroll
     for (int w = 0; w < WDB_NWARPS; ++w) {
@@ -138,37 +184,9 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
       woff += (w < (int)warp) ? c : 0u;
       ttotal += c;
     }
-
-    if (warp == 0) {  // decoupled look-back
-      i64 excl = 0;
-      if (tile == 0) {
-        if (lane == 0) wdb_st_status(&status[0], (WDB_ST_PREFIX << 62) | (u64)ttotal);
-      } else {
-        if (lane == 0) wdb_st_status(&status[tile], (WDB_ST_AGG << 62) | (u64)ttotal);
-        i64 look = tile - 1;
-        while (true) {
-          const i64 idx = look - (i64)lane;
-          u64 st = (WDB_ST_PREFIX << 62);
-          if (idx >= 0) {
-            do { st = wdb_ld_status(&status[idx]); } while ((st >> 62) == 0ull);
-          }
-          const u32 pm = __ballot_sync(WDB_FULL_MASK, (st >> 62) == WDB_ST_PREFIX);
-          const u64 v = st & WDB_ST_MASK;
-          if (pm) {
-            const u32 first = (u32)__ffs((int)pm) - 1u;
-            excl += (i64)wdb_warp_sum64(lane <= first ? v : 0ull);
-            break;
-          }
-          excl += (i64)wdb_warp_sum64(v);
-          look -= 32;
-        }
-        if (lane == 0) wdb_st_status(&status[tile], (WDB_ST_PREFIX << 62) | (u64)(excl + (i64)ttotal));
-      }
-      if (lane == 0) {
-        s_base = excl;
-        if (tile == ntiles - 1) *out_count = excl + (i64)ttotal;
-      }
-    }
+    // publish this tile's aggregate as early as possible
+    if (threadIdx.x == 0)
+      wdb_st_status(&status[tile], ((tile == 0 ? WDB_ST_PREFIX : WDB_ST_AGG) << 62) | (u64)ttotal);
 
     // stage survivors in row order
 #pragma unroll
@@ -184,7 +202,28 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
           ++pos;
         }
     }
-    __syncthreads();                                            // (3)
+
+    // issue the next tile's loads before waiting on the look-back: they complete while warp 0
+    // resolves this tile's offset and while the staged survivors are copied out
+    const bool next_full = next_tile < ntiles && (next_tile + 1) * WDB_TILE_ROWS <= n;
+    if (next_full) {
+      const i64 r0 = next_tile * WDB_TILE_ROWS + (i64)warp * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
+#pragma unroll
+      for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows(C, r0 + (i64)u * WDB_SLAB_ROWS, R[u]);
+    }
+
+    if (warp == 0) {
+      i64 excl = 0;
+      if (tile > 0) {
+        excl = wdb_lookback(status, tile, lane);
+        if (lane == 0) wdb_st_status(&status[tile], (WDB_ST_PREFIX << 62) | (u64)(excl + (i64)ttotal));
+      }
+      if (lane == 0) {
+        s_base = excl;
+        if (tile == ntiles - 1) *out_count = excl + (i64)ttotal;
+      }
+    }
+    __syncthreads();                                            // (B)
     const i64 g0 = s_base;
     // copy out with warps writing 128-byte aligned spans of the destination
     const int mis = (int)(g0 & 31);
@@ -195,6 +234,8 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
         out2[g0 + i] = s_stage2[i];
 #endif
       }
-    // the barriers (1) and (2) of the next iteration order these reads before the next staging
+    // barrier (A) of the next iteration orders these reads before the next staging writes
+    tile = next_tile;
+    full = next_full;
   }
 }

@@ -110,13 +110,31 @@ wdb_topk_scan(const wdb_cols C, const i64 n, const i64 row_base, float *__restri
     for (int u = 0; u < WDB_UNROLL; ++u) {
       if (!(full || v0 + (i64)u * WDB_BLOCK < nvec)) continue;
       const i64 row = (v0 + (i64)u * WDB_BLOCK) * WDB_VEC;
+      // Evaluate the whole vector, then test its best key against this thread's current worst
+      // once: after the first few tiles almost every vector is rejected by that single compare,
+      // so the per-row cost is the key expression plus one max/min (the kernel must stay under
+      // ~20 instructions per row to remain HBM-bound at 4 B/row).
+      float key[WDB_VEC];
+      float vbest = WDB_KEY_WORST;
 #pragma unroll
       for (int j = 0; j < WDB_VEC; ++j) {
+        key[j] = WDB_KEY(R[u], j);
 #if WDB_HAS_COND
-        if (!WDB_COND(R[u], j)) continue;
+        if (!WDB_COND(R[u], j)) key[j] = __int_as_float(0x7fc00000);   // NaN: never better than anything
 #endif
-        L.offer(WDB_KEY(R[u], j), row_base + row + j);
+#if WDB_DESC
+        vbest = fmaxf(vbest, key[j]);
+#else
+        vbest = fminf(vbest, key[j]);
+#endif
       }
+#if WDB_DESC
+      if (!(vbest >= L.k[WDB_K - 1])) continue;
+#else
+      if (!(vbest <= L.k[WDB_K - 1])) continue;
+#endif
+#pragma unroll
+      for (int j = 0; j < WDB_VEC; ++j) L.offer(key[j], row_base + row + j);
     }
   }
   if (blockIdx.x == 0) {

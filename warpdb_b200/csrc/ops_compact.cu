@@ -29,7 +29,7 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
   const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)vec * 4);
   spec.defines = {{"WDB_VEC", vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("compact.ld_hint", 0)},
                   {"WDB_ST_HINT", 0}, {"WDB_BLOCK", block}, {"WDB_UNROLL", unroll}, {"WDB_NOUT", two ? 2 : 1},
-                  {"WDB_THRESH", two ? thresh : 0}};
+                  {"WDB_THRESH", two ? thresh : 0}, {"WDB_MIN_CTAS", opt("compact.min_ctas", 1)}, {"WDB_LB", opt("compact.lookback", 4)}};
   spec.fns.push_back({"expr", "float", expr});
   if (two) spec.fns.push_back({"expr2", "float", expr2});
   spec.fns.push_back({"cond", "bool", cond});

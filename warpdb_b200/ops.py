@@ -152,9 +152,10 @@ def group_agg(table, val_expr, key_expr, cond=None, agg=wc.SUM, order=wc.ORDER_K
     """One-shot GROUP BY: returns (keys int32[G], vals float32[G])."""
     dev = _dev_index(table)
     n = num_rows(table)
-    cap = cap if cap is not None else max(min(n, 1 << 26), 1)
-    if expected_groups:
-        cap = max(min(cap, 2 * expected_groups + 16), 1)
+    if cap is None:
+        cap = max(min(n, 1 << 26), 1)
+        if expected_groups:
+            cap = max(min(cap, 2 * expected_groups + 16), 1)
     keys = torch.empty(cap, dtype=torch.int32, device=f"cuda:{dev}")
     vals = torch.empty(cap, dtype=torch.float32, device=f"cuda:{dev}")
     cols, nc = wc.make_cols(schema_of(table))
