@@ -315,9 +315,13 @@ def run_ours(args):
     value = world * rows * args.steps / (ms * 1e-3)
     ms_per_step = ms / args.steps
     achieved = w["bytes_per_row"] * rows / (ms_per_step * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+    # (profiles/traffic.json holds bytes per row measured on 2^28-row columns; scaled to this launch)
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(w["kernel"])
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"].get(w["kernel"])
+        if t and args.workload in ("projection", "topk5", "group1k"):
+            traffic = t["dram_bytes_per_row"] * rows
     except Exception:  # noqa: BLE001
         pass
     line = {

@@ -122,12 +122,16 @@ def sweep_compact(n):
         rec = {"name": "torch masked_select", "sel": cnt / n, "ms": ms, "gbs": gb / (ms * 1e-3)}
         print(json.dumps(rec), flush=True)
         f.write(json.dumps(rec) + "\n")
+        cfgs = []
+        for unroll, block, lb in itertools.product([2, 4], [256, 512], [1, 4]):
+            if block * 8 * unroll * 4 <= 46 * 1024:
+                cfgs.append({"variant": 0, "vec": 8, "unroll": unroll, "block": block, "min_ctas": 1, "lookback": lb, "ctas_per_sm": 8})
         for vec, unroll, block, minc, lb in itertools.product([4, 8], [1, 2, 4], [256, 512], [1, 2, 3, 4], [1, 4]):
-            if block * vec * unroll * 4 > 46 * 1024 or minc * block > 1024 * 2:
+            rows = block * vec * unroll
+            if rows < 2048 or 128 + rows * 12 > 200 * 1024 or minc * block > 2048:
                 continue
-            if lb == 1 and not (vec == 8 and unroll == 4):
-                continue
-            cfg = {"vec": vec, "unroll": unroll, "block": block, "min_ctas": minc, "lookback": lb, "ctas_per_sm": 8}
+            cfgs.append({"variant": 1, "vec": vec, "unroll": unroll, "block": block, "min_ctas": minc, "lookback": lb, "ctas_per_sm": 8})
+        for cfg in cfgs:
             for k, v in cfg.items():
                 wc.set_option("compact." + k, v)
             try:
@@ -188,3 +192,36 @@ if __name__ == "__main__":
         sweep_compact(int(float(sys.argv[2])) if len(sys.argv) > 2 else 1_000_000_000)
     elif what == "refjit":
         probe_refjit()
+
+
+def sweep_topk(n):
+    import torch
+    from warpdb_b200 import _core as wc, ops
+    wc.check(wc.lib().wdb_init(0))
+    wc.set_udf_source("__device__ float discount(float price, float rate) {\n    return price * rate;\n}\n")
+    price = ops.synth_f32(n, 0xC0FFEE + 5, 0.0, 1e6)
+    table = {"price": price}
+    f = open(os.path.join(OUT, "sweep_topk.jsonl"), "a")
+    pk = peak()
+    gb = 4.0 * n / 1e9
+    ms = time_op(lambda: torch.topk(price, 5), iters=5, warmup=1)
+    print(json.dumps({"name": "torch.topk", "ms": ms, "gbs": gb / (ms * 1e-3)}), flush=True)
+    ms = time_op(lambda: torch.max(price), iters=5, warmup=1)
+    print(json.dumps({"name": "torch.max (4 B/row streaming reduce)", "ms": ms, "gbs": gb / (ms * 1e-3)}), flush=True)
+    for vec, unroll, block, ctas in itertools.product([4, 8], [1, 2, 4], [256, 512], [2, 4, 8]):
+        cfg = {"vec": vec, "unroll": unroll, "block": block, "ctas_per_sm": ctas}
+        for k, v in cfg.items():
+            wc.set_option("topk." + k, v)
+        try:
+            ms = time_op(lambda: ops.topk(table, "discount(price[idx], 0.9f)", None, None, True, 5), iters=10)
+        except Exception as e:  # noqa: BLE001
+            print("FAILED", cfg, e, flush=True)
+            continue
+        rec = {"name": "wdb_topk k=5", "cfg": cfg, "ms": ms, "gbs": gb / (ms * 1e-3), "frac_measured_peak": gb / (ms * 1e-3) / pk, "rows": n}
+        print(json.dumps(rec), flush=True)
+        f.write(json.dumps(rec) + "\n")
+        f.flush()
+
+
+if __name__ == "__main__" and sys.argv[1] == "topk":
+    sweep_topk(int(float(sys.argv[2])) if len(sys.argv) > 2 else 2_000_000_000)

@@ -1,0 +1,382 @@
+// warpdb.cpp -- WarpDB facade on the B200-native core.
+//
+// Reference: src/warpdb.cpp.  query / query_multi_gpu / query_multi_gpu_csv / query_arrow follow
+// :199-257, :500-590.  query_sql at reference HEAD is two interleaved versions of itself and does
+// not compile; this implementation follows the semantics its tests pin (host path
+// "B": WHERE applied, fp64 accumulators, groups in key order, HAVING, DISTINCT, ORDER BY, OFFSET,
+// LIMIT -- tests/sql_features_test.cpp, tests/having_distinct_test.cpp) with every operator on the GPU.
+#include "warpdb.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cctype>
+#include <fstream>
+#include <memory>
+#include <stdexcept>
+#include <unordered_set>
+
+#include "multi_gpu_utils.hpp"
+#include "warpcore.h"
+
+namespace {
+
+[[noreturn]] void raise_core() { throw std::runtime_error(wdb_last_error()); }
+
+// every VariableNode must name a column: "Unknown column: x" (src/warpdb.cpp:19-44)
+void validate_ast(const ASTNode *node, const std::unordered_set<std::string> &cols) {
+  if (!node) return;
+  if (auto v = dynamic_cast<const VariableNode *>(node)) {
+    if (!cols.count(v->name)) throw std::runtime_error("Unknown column: " + v->name);
+  } else if (auto b = dynamic_cast<const BinaryOpNode *>(node)) {
+    validate_ast(b->left.get(), cols);
+    validate_ast(b->right.get(), cols);
+  } else if (auto f = dynamic_cast<const FunctionCallNode *>(node)) {
+    for (const auto &a : f->args) validate_ast(a.get(), cols);
+  } else if (auto a = dynamic_cast<const AggregationNode *>(node)) {
+    validate_ast(a->expr.get(), cols);
+  } else if (auto w = dynamic_cast<const WindowFunctionNode *>(node)) {
+    validate_ast(w->expr.get(), cols);
+    for (const auto &p : w->partition_by) validate_ast(p.get(), cols);
+    if (w->order_by) validate_ast(w->order_by->expr.get(), cols);
+  }
+}
+
+// "<expr> WHERE <cond>": the reference finds WHERE as a substring of the upper-cased text (:204-213)
+void split_where(const std::string &text, std::string *expr_part, std::string *where_part) {
+  std::string upper = text;
+  for (auto &c : upper) c = static_cast<char>(std::toupper(static_cast<unsigned char>(c)));
+  const auto pos = upper.find("WHERE");
+  if (pos == std::string::npos) {
+    *expr_part = text;
+    where_part->clear();
+  } else {
+    *expr_part = text.substr(0, pos);
+    *where_part = text.substr(pos + 5);
+  }
+}
+
+struct ParsedExpr { std::string expr_cuda, cond_cuda; };
+
+ParsedExpr parse_expr_where(const std::string &text, const std::unordered_set<std::string> &cols, bool wrap_errors) {
+  std::string expr_part, where_part;
+  split_where(text, &expr_part, &where_part);
+  ParsedExpr out;
+  ASTNodePtr expr_ast;
+  if (wrap_errors) {
+    try {
+      expr_ast = parse_expression(tokenize(expr_part));
+    } catch (const std::exception &e) {
+      throw std::runtime_error(std::string("Failed to parse expression: ") + e.what());
+    }
+  } else {
+    expr_ast = parse_expression(tokenize(expr_part));
+  }
+  validate_ast(expr_ast.get(), cols);
+  out.expr_cuda = expr_ast->to_cuda_expr();
+  if (!where_part.empty()) {
+    if (wrap_errors) {
+      try {
+        ASTNodePtr c = parse_expression(tokenize(where_part));
+        validate_ast(c.get(), cols);
+        out.cond_cuda = c->to_cuda_expr();
+      } catch (const std::exception &e) {
+        throw std::runtime_error(std::string("Failed to parse WHERE clause: ") + e.what());
+      }
+    } else {
+      ASTNodePtr c = parse_expression(tokenize(where_part));
+      validate_ast(c.get(), cols);
+      out.cond_cuda = c->to_cuda_expr();
+    }
+  }
+  return out;
+}
+
+std::vector<wdb_col_t> describe(const Table &t) {
+  std::vector<wdb_col_t> cols;
+  for (const auto &c : t.columns) cols.push_back(wdb_col_t{c.name.c_str(), static_cast<int>(c.type), c.device_ptr, t.num_rows});
+  return cols;
+}
+
+void refresh_udf_source() {   // ./custom.cu is re-read on every call (src/jit.cpp:65-73)
+  std::ifstream in("custom.cu");
+  std::string src;
+  if (in) src.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+  wdb_set_udf_source(src.c_str());
+}
+
+struct DeviceBuffer {
+  void *p = nullptr;
+  explicit DeviceBuffer(size_t bytes) {
+    if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) throw std::runtime_error("CUDA error: out of memory");
+  }
+  ~DeviceBuffer() { if (p) cudaFree(p); }
+  DeviceBuffer(const DeviceBuffer &) = delete;
+  DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+  template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+template <class T> std::vector<T> download(const void *d, size_t n) {
+  std::vector<T> h(n);
+  if (n && cudaMemcpy(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost) != cudaSuccess) throw std::runtime_error("CUDA error: download failed");
+  return h;
+}
+
+// HAVING over one group (float arithmetic like eval_having_node, src/warpdb.cpp:387-417)
+struct GroupRow { double sum, count, mn, mx; };
+float eval_having(const ASTNode *n, const GroupRow &g) {
+  if (auto c = dynamic_cast<const ConstantNode *>(n)) return std::stof(c->value);
+  if (auto b = dynamic_cast<const BinaryOpNode *>(n)) {
+    const float l = eval_having(b->left.get(), g), r = eval_having(b->right.get(), g);
+    const std::string &op = b->op;
+    if (op == "+") return l + r;
+    if (op == "-") return l - r;
+    if (op == "*") return l * r;
+    if (op == "/") return l / r;
+    if (op == ">") return l > r;
+    if (op == "<") return l < r;
+    if (op == ">=") return l >= r;
+    if (op == "<=") return l <= r;
+    if (op == "==") return l == r;
+    if (op == "!=") return l != r;
+    if (op == "&&") return (l != 0.0f) && (r != 0.0f);
+    if (op == "||") return (l != 0.0f) || (r != 0.0f);
+    return 0.0f;
+  }
+  if (auto a = dynamic_cast<const AggregationNode *>(n)) {
+    switch (a->agg) {
+    case AggregationType::Sum: return static_cast<float>(g.sum);
+    case AggregationType::Avg: return static_cast<float>(g.sum / g.count);
+    case AggregationType::Count: return static_cast<float>(g.count);
+    case AggregationType::Min: return static_cast<float>(g.mn);
+    case AggregationType::Max: return static_cast<float>(g.mx);
+    }
+  }
+  return 0.0f;
+}
+int needs_of(AggregationType a) {
+  switch (a) {
+  case AggregationType::Sum: return WDB_NEED_SUM;
+  case AggregationType::Avg: return WDB_NEED_SUM | WDB_NEED_COUNT;
+  case AggregationType::Count: return WDB_NEED_COUNT;
+  case AggregationType::Min: case AggregationType::Max: return WDB_NEED_MINMAX;
+  }
+  return 0;
+}
+void collect_needs(const ASTNode *n, int *needs) {
+  if (!n) return;
+  if (auto a = dynamic_cast<const AggregationNode *>(n)) *needs |= needs_of(a->agg);
+  else if (auto b = dynamic_cast<const BinaryOpNode *>(n)) { collect_needs(b->left.get(), needs); collect_needs(b->right.get(), needs); }
+}
+float group_result(AggregationType a, const GroupRow &g) {   // src/warpdb.cpp:429-435
+  switch (a) {
+  case AggregationType::Sum: return static_cast<float>(g.sum);
+  case AggregationType::Avg: return static_cast<float>(g.sum / g.count);
+  case AggregationType::Count: return static_cast<float>(g.count);
+  case AggregationType::Min: return static_cast<float>(g.mn);
+  case AggregationType::Max: return static_cast<float>(g.mx);
+  }
+  return 0.0f;
+}
+void sort_unique(std::vector<float> &v) {   // src/warpdb.cpp:463-468
+  std::sort(v.begin(), v.end());
+  v.erase(std::unique(v.begin(), v.end()), v.end());
+}
+void apply_offset_limit(std::vector<float> &r, const QueryAST &q) {   // src/warpdb.cpp:485-495
+  if (q.offset) {
+    const size_t off = static_cast<size_t>(std::max(q.offset->count, 0));
+    if (off >= r.size()) r.clear();
+    else r.erase(r.begin(), r.begin() + static_cast<std::ptrdiff_t>(off));
+  }
+  if (q.limit && static_cast<size_t>(std::max(q.limit->count, 0)) < r.size()) r.resize(static_cast<size_t>(std::max(q.limit->count, 0)));
+}
+
+}  // namespace
+
+WarpDB::WarpDB(const std::string &filepath, const std::vector<DataType> &schema) {
+  const auto dot = filepath.find_last_of('.');
+  std::string ext = dot == std::string::npos ? "" : filepath.substr(dot + 1);
+  for (auto &c : ext) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
+  if (ext == "csv") {
+    host_table_ = load_csv_to_host(filepath, schema);
+    table_ = upload_to_gpu(host_table_);
+  } else if (ext == "json") {
+    host_table_ = load_json_to_host(filepath);
+    table_ = upload_to_gpu(host_table_);
+  } else if (ext == "parquet" || ext == "arrow" || ext == "feather" || ext == "orc") {
+    throw std::runtime_error("Arrow support is not compiled into WarpDB");   // src/warpdb.cpp:181-184
+  } else {
+    throw std::runtime_error("Unsupported file format: " + filepath);
+  }
+}
+
+WarpDB::WarpDB(Table device_table, HostTable host_table)
+    : table_(std::move(device_table)), host_table_(std::move(host_table)), owns_device_(false) {}
+
+WarpDB::~WarpDB() {
+  if (owns_device_) free_table(table_);
+}
+
+std::vector<float> WarpDB::query(const std::string &expr) {
+  if (expr.empty()) throw std::runtime_error("Empty query expression");
+  std::unordered_set<std::string> cols;
+  for (const auto &c : table_.columns) cols.insert(c.name);
+  const ParsedExpr p = parse_expr_where(expr, cols, true);
+  refresh_udf_source();
+  const size_t n = static_cast<size_t>(table_.num_rows);
+  DeviceBuffer out(sizeof(float) * n);
+  const std::vector<wdb_col_t> dcols = describe(table_);
+  int64_t count = 0;
+  // the reference leaves rows failing WHERE uninitialised in a fresh cudaMalloc buffer
+  // (src/jit.cpp:55-61, src/warpdb.cpp:243-256); they are defined as 0.0f here
+  if (wdb_project_filter(0, nullptr, dcols.data(), static_cast<int>(dcols.size()), p.expr_cuda.c_str(), p.cond_cuda.c_str(),
+                         out.as<float>(), table_.num_rows, WDB_DENSE_ZERO, nullptr, &count))
+    raise_core();
+  return download<float>(out.p, n);
+}
+
+std::vector<float> WarpDB::query_sql(const std::string &sql) {
+  const std::vector<Token> tokens = tokenize(sql);
+  QueryAST ast;
+  try {
+    ast = parse_query_extended(tokens);
+  } catch (const std::exception &e) {
+    throw std::runtime_error(std::string("Failed to parse SQL: ") + e.what());
+  }
+  std::unordered_set<std::string> cols;
+  for (const auto &c : table_.columns) cols.insert(c.name);
+  auto validate_ctx = [&](const ASTNode *node, const char *ctx) {
+    try {
+      validate_ast(node, cols);
+    } catch (const std::exception &e) {
+      throw std::runtime_error(std::string(ctx) + ": " + e.what());
+    }
+  };
+  for (const auto &e : ast.select_list) validate_ctx(e.get(), "SELECT clause");
+  for (const auto &j : ast.joins) validate_ctx(j.condition.get(), "JOIN condition");
+  if (ast.where) validate_ctx(ast.where->get(), "WHERE clause");
+  if (ast.group_by)
+    for (const auto &k : ast.group_by->keys) validate_ctx(k.get(), "GROUP BY");
+  if (ast.order_by) validate_ctx(ast.order_by->expr.get(), "ORDER BY");
+  if (ast.select_list.empty()) throw std::runtime_error("Empty select list");
+
+  refresh_udf_source();
+  const std::vector<wdb_col_t> dcols = describe(table_);
+  const int nc = static_cast<int>(dcols.size());
+  const int64_t n = table_.num_rows;
+  const std::string cond = ast.where ? (*ast.where)->to_cuda_expr() : std::string();
+  std::vector<float> result;
+
+  if (ast.group_by) {
+    auto *agg = dynamic_cast<AggregationNode *>(ast.select_list[0].get());
+    if (!agg) throw std::runtime_error("Only aggregation queries supported with GROUP BY");   // src/warpdb.cpp:353
+    if (ast.group_by->keys.empty()) throw std::runtime_error("GROUP BY needs a key");
+    int needs = needs_of(agg->agg);
+    if (ast.having) collect_needs(ast.having->get(), &needs);
+    const std::string val = agg->expr->to_cuda_expr(), key = ast.group_by->keys[0]->to_cuda_expr();
+    // groups come back in key order (std::map, src/warpdb.cpp:425); ORDER BY with GROUP BY sorts by
+    // key in the requested direction whatever its expression is (jit_sort_pairs, :370-371)
+    const int order = (ast.order_by && !ast.order_by->ascending) ? WDB_ORDER_KEY_DESC : WDB_ORDER_KEY_ASC;
+    int64_t expect = 1 << 16, groups = 0;
+    for (int attempt = 0;; ++attempt) {
+      wdb_agg_t *t = nullptr;
+      if (wdb_agg_create(0, expect, needs, &t)) raise_core();
+      std::unique_ptr<wdb_agg_t, int (*)(wdb_agg_t *)> guard(t, wdb_agg_destroy);
+      if (wdb_agg_consume(t, nullptr, dcols.data(), nc, val.c_str(), key.c_str(), cond.c_str(), n, 0)) raise_core();
+      if (wdb_agg_size(t, nullptr, &groups)) {
+        const std::string msg = wdb_last_error();
+        if (msg.find("table overflow") != std::string::npos && attempt < 5) { expect *= 16; continue; }
+        throw std::runtime_error(msg);
+      }
+      const size_t g = static_cast<size_t>(groups);
+      DeviceBuffer sums(8 * g), counts(8 * g), mins(8 * g), maxs(8 * g);
+      if (wdb_agg_export(t, nullptr, static_cast<int>(agg->agg), order, nullptr, nullptr, (needs & WDB_NEED_SUM) ? sums.as<double>() : nullptr,
+                         (needs & WDB_NEED_COUNT) ? counts.as<int64_t>() : nullptr, (needs & WDB_NEED_MINMAX) ? mins.as<double>() : nullptr,
+                         (needs & WDB_NEED_MINMAX) ? maxs.as<double>() : nullptr, nullptr, groups, &groups))
+        raise_core();
+      std::vector<double> hs, hmn, hmx;
+      std::vector<int64_t> hc;
+      if (needs & WDB_NEED_SUM) hs = download<double>(sums.p, g);
+      if (needs & WDB_NEED_COUNT) hc = download<int64_t>(counts.p, g);
+      if (needs & WDB_NEED_MINMAX) { hmn = download<double>(mins.p, g); hmx = download<double>(maxs.p, g); }
+      for (size_t i = 0; i < g; ++i) {
+        const GroupRow row{hs.empty() ? 0.0 : hs[i], hc.empty() ? 0.0 : static_cast<double>(hc[i]), hmn.empty() ? 0.0 : hmn[i],
+                           hmx.empty() ? 0.0 : hmx[i]};
+        if (ast.having && eval_having(ast.having->get(), row) == 0.0f) continue;
+        result.push_back(group_result(agg->agg, row));
+      }
+      break;
+    }
+    if (ast.distinct) sort_unique(result);
+    apply_offset_limit(result, ast);
+    return result;
+  }
+
+  const std::string sel = ast.select_list[0]->to_cuda_expr();
+  const bool same_order_expr = ast.order_by && ast.order_by->expr->to_cuda_expr() == sel;
+  if (ast.distinct) {
+    if (ast.order_by && !same_order_expr) throw std::runtime_error("DISTINCT with ORDER BY on a different expression is not supported");
+    DeviceBuffer out(sizeof(float) * static_cast<size_t>(n));
+    int64_t count = 0;
+    if (wdb_project_filter(0, nullptr, dcols.data(), nc, sel.c_str(), cond.c_str(), out.as<float>(), n, WDB_COMPACT, nullptr, &count)) raise_core();
+    if (wdb_sort_float(0, nullptr, out.as<float>(), count, 1)) raise_core();
+    result = download<float>(out.p, static_cast<size_t>(count));
+    result.erase(std::unique(result.begin(), result.end()), result.end());
+    if (ast.order_by && !ast.order_by->ascending) std::reverse(result.begin(), result.end());
+    apply_offset_limit(result, ast);
+    return result;
+  }
+  if (ast.order_by) {   // ORDER BY e [LIMIT k] [OFFSET o]: stable sort of the survivors, then the slice
+    const int64_t k = ast.limit ? std::max(ast.limit->count, 0) : -1;
+    const int64_t off = ast.offset ? std::max(ast.offset->count, 0) : 0;
+    const int64_t cap = k < 0 ? n : std::min<int64_t>(k, n);
+    DeviceBuffer out(sizeof(float) * static_cast<size_t>(std::max<int64_t>(cap, 1)));
+    int64_t m = 0;
+    if (wdb_topk(0, nullptr, dcols.data(), nc, ast.order_by->expr->to_cuda_expr().c_str(), sel.c_str(), cond.c_str(),
+                 ast.order_by->ascending ? 0 : 1, k, off, n, out.as<float>(), nullptr, &m))
+      raise_core();
+    return download<float>(out.p, static_cast<size_t>(m));
+  }
+  // plain SELECT: surviving rows in row order (stable compaction), then OFFSET / LIMIT
+  DeviceBuffer out(sizeof(float) * static_cast<size_t>(n));
+  int64_t count = 0;
+  if (wdb_project_filter(0, nullptr, dcols.data(), nc, sel.c_str(), cond.c_str(), out.as<float>(), n, WDB_COMPACT, nullptr, &count)) raise_core();
+  const int64_t off = std::min<int64_t>(ast.offset ? std::max(ast.offset->count, 0) : 0, count);
+  int64_t m = count - off;
+  if (ast.limit) m = std::min<int64_t>(m, std::max(ast.limit->count, 0));
+  return download<float>(out.as<float>() + off, static_cast<size_t>(m));
+}
+
+void WarpDB::query_arrow(const std::string &expr, ArrowArray *out_array, ArrowSchema *out_schema, bool use_shared_memory) {
+  const std::vector<float> result = query(expr);
+  export_to_arrow(result.data(), static_cast<int64_t>(result.size()), use_shared_memory, out_array, out_schema);
+}
+
+std::vector<float> WarpDB::query_multi_gpu(const std::string &expr) {
+  if (host_table_.num_rows() == 0) throw std::runtime_error("Host table not available for multi-GPU query");   // :509-511
+  std::unordered_set<std::string> cols;   // the reference hard-codes {"price","quantity"} (:528); the table's own columns are used
+  for (const auto &c : host_table_.columns) cols.insert(c.name);
+  const ParsedExpr p = parse_expr_where(expr, cols, false);
+  refresh_udf_source();
+  return run_multi_gpu_jit_host(host_table_, p.expr_cuda, p.cond_cuda);
+}
+
+std::vector<float> WarpDB::query_multi_gpu_csv(const std::string &csv_path, const std::string &expr, int rows_per_chunk) {
+  std::ifstream file(csv_path);
+  if (!file.is_open()) throw std::runtime_error("Failed to open file: " + csv_path);   // :573-575
+  std::string header;
+  std::getline(file, header);
+  const std::vector<std::string> names = split_csv_header(header);
+  std::unordered_set<std::string> cols(names.begin(), names.end());
+  const ParsedExpr p = parse_expr_where(expr, cols, false);
+  refresh_udf_source();
+  bool finished = false;
+  std::vector<float> all;
+  while (!finished) {
+    HostTable chunk = load_csv_chunk(file, rows_per_chunk, finished, names);
+    if (chunk.num_rows() == 0) break;
+    const std::vector<float> part = run_multi_gpu_jit_host(chunk, p.expr_cuda, p.cond_cuda);
+    all.insert(all.end(), part.begin(), part.end());
+  }
+  return all;
+}

@@ -1,0 +1,40 @@
+// warpdb.hpp -- the WarpDB facade with the reference's public signatures (include/warpdb.hpp:11-48),
+// running on the B200-native core (include/warpcore.h).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "arrow_utils.hpp"
+#include "csv_loader.hpp"
+#include "expression.hpp"
+#include "jit.hpp"
+
+class WarpDB {
+public:
+  // .csv (optional explicit schema; default every column Float32) or .json (NDJSON price/quantity)
+  explicit WarpDB(const std::string &filepath, const std::vector<DataType> &schema = {});
+  // adopt columns that already live on the device (benchmarks, sharded tables); not in the reference
+  explicit WarpDB(Table device_table, HostTable host_table = {});
+  ~WarpDB();
+  WarpDB(const WarpDB &) = delete;
+  WarpDB &operator=(const WarpDB &) = delete;
+
+  // "<expr> [WHERE <cond>]" -> one float per table row; rows failing cond yield 0.0f
+  std::vector<float> query(const std::string &expr);
+  // SELECT [DISTINCT] <expr|AGG(expr)> FROM t [WHERE c] [GROUP BY k] [HAVING h] [ORDER BY e [ASC|DESC]] [LIMIT n] [OFFSET m]
+  std::vector<float> query_sql(const std::string &sql);
+  // same as query() over every visible GPU (row-range shards of the host copy of the table)
+  std::vector<float> query_multi_gpu(const std::string &expr);
+  // stream a CSV in chunks of rows_per_chunk rows through all GPUs
+  static std::vector<float> query_multi_gpu_csv(const std::string &csv_path, const std::string &expr, int rows_per_chunk = 1000000);
+  // query() exported through the Arrow C data interface
+  void query_arrow(const std::string &expr, ArrowArray *out_array, ArrowSchema *out_schema, bool use_shared_memory = false);
+
+  int num_rows() const { return table_.num_rows; }
+  const Table &table() const { return table_; }
+
+private:
+  Table table_;
+  HostTable host_table_;
+  bool owns_device_ = true;
+};

@@ -7,6 +7,9 @@
 // a decoupled look-back over 64-bit tile status words, so the packed output is written once, fully
 // coalesced and in row order.
 //
+// Two kernels: wdb_compact (register-staged vector loads, tiles handed out by an atomic ticket) and
+// wdb_compact_bulk (TMA bulk copies into a shared-memory ring, static tile assignment).
+//
 // Roofline: HBM.  Algorithmic bytes per row = sum(sizeof used columns) + 4*WDB_NOUT*selectivity.
 //
 // Host-supplied macros: WDB_BLOCK, WDB_UNROLL (slabs per warp per tile), WDB_VEC, WDB_NOUT (1|2),
@@ -44,10 +47,11 @@ __device__ __forceinline__ u64 wdb_warp_sum64(u64 v) {
   return v;
 }
 
+
 // Decoupled look-back over a window of 32*WDB_LB predecessor tiles per step: lane l inspects the
-// WDB_LB status words of tiles look-(l*WDB_LB+q).  Returns the exclusive prefix of `tile`.
+// WDB_LB status words of tiles look-(l*WDB_LB+q).  Returns the exclusive prefix of `tile` (> 0).
 #ifndef WDB_LB
-#define WDB_LB 4
+#define WDB_LB 1
 #endif
 __device__ __forceinline__ i64 wdb_lookback(const u64 *__restrict__ status, const i64 tile, const u32 lane) {
   i64 excl = 0;
@@ -58,7 +62,7 @@ __device__ __forceinline__ i64 wdb_lookback(const u64 *__restrict__ status, cons
 #pragma unroll
     for (int q = 0; q < WDB_LB; ++q) {
       const i64 idx = look - ((i64)lane * WDB_LB + q);
-      u64 st = (WDB_ST_PREFIX << 62);              // tiles before the first one: prefix 0
+      u64 st = (WDB_ST_PREFIX << 62);              // before the first tile: prefix 0
       if (idx >= 0) {
         do { st = wdb_ld_status(&status[idx]); } while ((st >> 62) == 0ull);
       }
@@ -70,18 +74,16 @@ __device__ __forceinline__ i64 wdb_lookback(const u64 *__restrict__ status, cons
     const u32 pm = __ballot_sync(WDB_FULL_MASK, has_prefix);
     if (pm) {
       const u32 first = (u32)__ffs((int)pm) - 1u;
-      excl += (i64)wdb_warp_sum64(lane <= first ? part : 0ull);
-      return excl;
+      return excl + (i64)wdb_warp_sum64(lane <= first ? part : 0ull);
     }
     excl += (i64)wdb_warp_sum64(part);
     look -= 32 * WDB_LB;
   }
 }
 
-#ifndef WDB_MIN_CTAS
-#define WDB_MIN_CTAS 1
-#endif
-extern "C" __global__ void __launch_bounds__(WDB_BLOCK, WDB_MIN_CTAS)
+#if !WDB_BULK
+// ---- variant 0: register-staged vector loads, tiles handed out in ticket order
+extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
 wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n,
             u64 *__restrict__ status, u32 *__restrict__ ticket, i64 *__restrict__ out_count, const i64 ntiles,
             const float wdb_tau, const i64 out_cap) {
@@ -91,26 +93,15 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
 #endif
   __shared__ u32 s_wcount[WDB_NWARPS];
   __shared__ i64 s_base;
-  __shared__ u32 s_tile[2];
+  __shared__ u32 s_tile;
   const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const u32 lt = wdb_lanemask_lt();
 
-  // Tiles are handed out in ticket order, so every predecessor of a tile is owned by a CTA that is
-  // already running: the look-back can never wait on work that has not been scheduled.
-  if (threadIdx.x == 0) s_tile[0] = atomicAdd(ticket, 1u);
-  __syncthreads();
-  i64 tile = (i64)s_tile[0];
-  wdb_rows R[WDB_UNROLL];
-  bool full = tile < ntiles && (tile + 1) * WDB_TILE_ROWS <= n;
-  if (full) {
-    const i64 r0 = tile * WDB_TILE_ROWS + (i64)warp * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
-#pragma unroll
-    for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows(C, r0 + (i64)u * WDB_SLAB_ROWS, R[u]);
-  }
-
-  for (u32 it = 0; tile < ntiles; ++it) {
-    // the next ticket is requested now and read after the barrier below: its latency is hidden
-    if (threadIdx.x == 0) s_tile[(it + 1u) & 1u] = atomicAdd(ticket, 1u);
+  while (true) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();                                            // (1)
+    const i64 tile = (i64)s_tile;
+    if (tile >= ntiles) break;
     const i64 wrow0 = tile * WDB_TILE_ROWS + (i64)warp * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
 
     u32 flags[WDB_UNROLL];
@@ -118,7 +109,10 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
 #if WDB_NOUT == 2
     float vals2[WDB_UNROLL][WDB_VEC];
 #endif
-    if (full) {
+    if ((tile + 1) * WDB_TILE_ROWS <= n) {
+      wdb_rows R[WDB_UNROLL];
+#pragma unroll
+      for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows(C, wrow0 + (i64)u * WDB_SLAB_ROWS, R[u]);
 #pragma unroll
       for (int u = 0; u < WDB_UNROLL; ++u) {
         u32 m = 0;
@@ -132,7 +126,183 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
         }
         flags[u] = m;
       }
-    } else {  // ragged last tile
+    } else {
+#pragma unroll
+      for (int u = 0; u < WDB_UNROLL; ++u) {
+        u32 m = 0;
+#pragma unroll
+        for (int j = 0; j < WDB_VEC; ++j) {
+          const i64 row = wrow0 + (i64)u * WDB_SLAB_ROWS + j;
+          vals[u][j] = 0.0f;
+#if WDB_NOUT == 2
+          vals2[u][j] = 0.0f;
+#endif
+          if (row < n) {
+            wdb_rows R;
+            wdb_load_row1(C, row, R, 0);
+            if (WDB_KEEP(R, 0)) {
+              m |= 1u << j;
+              vals[u][j] = WDB_EXPR(R, 0);
+#if WDB_NOUT == 2
+              vals2[u][j] = WDB_EXPR2(R, 0);
+#endif
+            }
+          }
+        }
+        flags[u] = m;
+      }
+    }
+
+    // rank of this lane's first survivor inside the warp's region: ballots give, per element slot
+    // j, the set of lanes that keep it; rows are ordered (slab, lane, j)
+    u32 rank[WDB_UNROLL], wtotal = 0;
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) {
+      u32 pre = 0, tot = 0;
+#pragma unroll
+      for (int j = 0; j < WDB_VEC; ++j) {
+        const u32 b = __ballot_sync(WDB_FULL_MASK, (flags[u] >> j) & 1u);
+        pre += __popc(b & lt);
+        tot += __popc(b);
+      }
+      rank[u] = wtotal + pre;
+      wtotal += tot;
+    }
+    if (lane == 0) s_wcount[warp] = wtotal;
+    __syncthreads();                                            // (2)
+    u32 woff = 0, ttotal = 0;
+#pragma unroll
+    for (int w = 0; w < WDB_NWARPS; ++w) {
+      const u32 c = s_wcount[w];
+      woff += (w < (int)warp) ? c : 0u;
+      ttotal += c;
+    }
+
+    if (warp == 0) {  // decoupled look-back
+      i64 excl = 0;
+      if (tile == 0) {
+        if (lane == 0) wdb_st_status(&status[0], (WDB_ST_PREFIX << 62) | (u64)ttotal);
+      } else {
+        if (lane == 0) wdb_st_status(&status[tile], (WDB_ST_AGG << 62) | (u64)ttotal);
+        excl = wdb_lookback(status, tile, lane);
+        if (lane == 0) wdb_st_status(&status[tile], (WDB_ST_PREFIX << 62) | (u64)(excl + (i64)ttotal));
+      }
+      if (lane == 0) {
+        s_base = excl;
+        if (tile == ntiles - 1) *out_count = excl + (i64)ttotal;
+      }
+    }
+
+    // stage survivors in row order
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) {
+      u32 pos = woff + rank[u];
+#pragma unroll
+      for (int j = 0; j < WDB_VEC; ++j)
+        if ((flags[u] >> j) & 1u) {
+          s_stage[pos] = vals[u][j];
+#if WDB_NOUT == 2
+          s_stage2[pos] = vals2[u][j];
+#endif
+          ++pos;
+        }
+    }
+    __syncthreads();                                            // (3)
+    const i64 g0 = s_base;
+    // copy out with warps writing 128-byte aligned spans of the destination
+    const int mis = (int)(g0 & 31);
+    for (int i = (int)threadIdx.x - mis; i < (int)ttotal; i += WDB_BLOCK)
+      if (i >= 0 && g0 + i < out_cap) {   // the count stays exact when the output is too small
+        out[g0 + i] = s_stage[i];
+#if WDB_NOUT == 2
+        out2[g0 + i] = s_stage2[i];
+#endif
+      }
+    // the barriers (1) and (2) of the next iteration order these reads before the next staging
+  }
+}
+
+#endif  // !WDB_BULK
+
+#if WDB_BULK
+// ---- variant 1: the same algorithm with the column tiles streamed into a double-buffered shared
+// memory ring by bulk asynchronous copies (TMA 1-D, cp.async.bulk -> UBLKCP).  The tile after the
+// current one is in flight for the whole time this CTA ranks, resolves its offset and copies out,
+// so the serial latency chain of a tile (load -> rank -> look-back -> copy-out) no longer leaves
+// HBM idle, and the loaded data no longer lives in registers across barriers.  Tiles are assigned
+// statically (tile = blockIdx.x + k*gridDim.x) so the next tile is known without a ticket; the grid
+// never exceeds the number of co-resident CTAs, hence every predecessor of a tile is running.
+#ifndef WDB_MIN_CTAS
+#define WDB_MIN_CTAS 1
+#endif
+extern "C" __global__ void __launch_bounds__(WDB_BLOCK, WDB_MIN_CTAS)
+wdb_compact_bulk(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n,
+                 u64 *__restrict__ status, i64 *__restrict__ out_count, const i64 ntiles,
+                 const float wdb_tau, const i64 out_cap) {
+  extern __shared__ __align__(128) unsigned char wdb_smem[];
+  u64 *full = reinterpret_cast<u64 *>(wdb_smem);                         // 2 mbarriers
+  unsigned char *in0 = wdb_smem + 128;                                   // 2 x WDB_IN_BYTES
+  float *s_stage = reinterpret_cast<float *>(in0 + 2 * (size_t)WDB_IN_BYTES);
+#if WDB_NOUT == 2
+  float *s_stage2 = s_stage + WDB_TILE_ROWS;
+#endif
+  __shared__ u32 s_wcount[WDB_NWARPS];
+  __shared__ i64 s_base;
+  const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const u32 lt = wdb_lanemask_lt();
+  const i64 nfull = n / WDB_TILE_ROWS;                                   // tiles that can be bulk-loaded
+
+  if (threadIdx.x == 0) {
+    wdb_mbar_init(&full[0], 1);
+    wdb_mbar_init(&full[1], 1);
+    wdb_fence_barrier_init();
+    wdb_fence_proxy_async();
+  }
+  __syncthreads();
+  const i64 first = blockIdx.x, step = gridDim.x;
+  if (threadIdx.x == 0 && first < nfull) {
+    wdb_mbar_expect_tx(&full[0], WDB_IN_BYTES);
+    wdb_bulk_load_tile(C, first * WDB_TILE_ROWS, in0, &full[0]);
+  }
+
+  u32 it = 0;
+  for (i64 tile = first; tile < ntiles; tile += step, ++it) {
+    const u32 buf = it & 1u;
+    // the other buffer was last read before barrier (A) of the previous iteration: refill it now
+    if (threadIdx.x == 0 && tile + step < nfull) {
+      wdb_mbar_expect_tx(&full[buf ^ 1u], WDB_IN_BYTES);
+      wdb_bulk_load_tile(C, (tile + step) * WDB_TILE_ROWS, in0 + (size_t)(buf ^ 1u) * WDB_IN_BYTES, &full[buf ^ 1u]);
+    }
+    const int lrow0 = (int)(warp * WDB_WARP_ROWS + lane * WDB_VEC);       // row inside the tile
+
+    u32 flags[WDB_UNROLL];
+    float vals[WDB_UNROLL][WDB_VEC];
+#if WDB_NOUT == 2
+    float vals2[WDB_UNROLL][WDB_VEC];
+#endif
+    if (tile < nfull) {
+      wdb_mbar_wait(&full[buf], (it >> 1) & 1u);
+      const unsigned char *sb = in0 + (size_t)buf * WDB_IN_BYTES;
+#pragma unroll
+      for (int u = 0; u < WDB_UNROLL; ++u) {
+        u32 m = 0;
+#pragma unroll
+        for (int h = 0; h < WDB_VEC / 4; ++h) {
+          wdb_rows4s R4;
+          wdb_lds_rows(sb, lrow0 + u * WDB_SLAB_ROWS + 4 * h, R4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            m |= (WDB_KEEP(R4, j) ? 1u : 0u) << (4 * h + j);
+            vals[u][4 * h + j] = WDB_EXPR(R4, j);
+#if WDB_NOUT == 2
+            vals2[u][4 * h + j] = WDB_EXPR2(R4, j);
+#endif
+          }
+        }
+        flags[u] = m;
+      }
+    } else {  // ragged last tile: guarded direct loads
+      const i64 wrow0 = tile * WDB_TILE_ROWS + lrow0;
 #pragma unroll
       for (int u = 0; u < WDB_UNROLL; ++u) {
         u32 m = 0;
@@ -159,8 +329,6 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
       }
     }
 
-    // rank of this lane's first survivor inside the warp's region: ballots give, per element slot
-    // j, the set of lanes that keep it; rows are ordered (slab, lane, j)
     u32 rank[WDB_UNROLL], wtotal = 0;
 #pragma unroll
     for (int u = 0; u < WDB_UNROLL; ++u) {
@@ -176,7 +344,6 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
     }
     if (lane == 0) s_wcount[warp] = wtotal;
     __syncthreads();                                            // (A)
-    const i64 next_tile = (i64)s_tile[(it + 1u) & 1u];
     u32 woff = 0, ttotal = 0;
 #pragma unroll
     for (int w = 0; w < WDB_NWARPS; ++w) {
@@ -184,11 +351,8 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
       woff += (w < (int)warp) ? c : 0u;
       ttotal += c;
     }
-    // publish this tile's aggregate as early as possible
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0)   // publish the aggregate before anything else
       wdb_st_status(&status[tile], ((tile == 0 ? WDB_ST_PREFIX : WDB_ST_AGG) << 62) | (u64)ttotal);
-
-    // stage survivors in row order
 #pragma unroll
     for (int u = 0; u < WDB_UNROLL; ++u) {
       u32 pos = woff + rank[u];
@@ -202,16 +366,6 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
           ++pos;
         }
     }
-
-    // issue the next tile's loads before waiting on the look-back: they complete while warp 0
-    // resolves this tile's offset and while the staged survivors are copied out
-    const bool next_full = next_tile < ntiles && (next_tile + 1) * WDB_TILE_ROWS <= n;
-    if (next_full) {
-      const i64 r0 = next_tile * WDB_TILE_ROWS + (i64)warp * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
-#pragma unroll
-      for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows(C, r0 + (i64)u * WDB_SLAB_ROWS, R[u]);
-    }
-
     if (warp == 0) {
       i64 excl = 0;
       if (tile > 0) {
@@ -225,17 +379,15 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
     }
     __syncthreads();                                            // (B)
     const i64 g0 = s_base;
-    // copy out with warps writing 128-byte aligned spans of the destination
     const int mis = (int)(g0 & 31);
     for (int i = (int)threadIdx.x - mis; i < (int)ttotal; i += WDB_BLOCK)
-      if (i >= 0 && g0 + i < out_cap) {   // the count stays exact when the output is too small
+      if (i >= 0 && g0 + i < out_cap) {
         out[g0 + i] = s_stage[i];
 #if WDB_NOUT == 2
         out2[g0 + i] = s_stage2[i];
 #endif
       }
     // barrier (A) of the next iteration orders these reads before the next staging writes
-    tile = next_tile;
-    full = next_full;
   }
 }
+#endif

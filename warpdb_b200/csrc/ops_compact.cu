@@ -5,7 +5,7 @@
 
 namespace wdb {
 
-struct CompactPlan { GenSpec spec; int block, unroll, vec; int64_t tile_rows; bool two; };
+struct CompactPlan { GenSpec spec; int block, unroll, vec, variant; int64_t tile_rows; bool two; size_t smem; };
 
 static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, const char *expr2, const char *cond,
                         bool check_alignment, int thresh, CompactPlan *p) {
@@ -19,17 +19,27 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
     if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
   const int block = (int)opt("compact.block", 256), vec = (int)opt("compact.vec", 8);
   int unroll = (int)opt("compact.unroll", 4);
-  while (two && unroll > 1 && (int64_t)block * vec * unroll * 8 > 46 * 1024) unroll /= 2;   // two staging buffers
+  int variant = (int)opt("compact.variant", 1);   // 0 ticket + register loads, 1 TMA bulk ring
   if (vec != 4 && vec != 8) return fail("compact.vec must be 4 or 8");
   if (block < 32 || block > 1024 || (block & 31)) return fail("compact.block must be a multiple of 32 in [32,1024]");
   if (unroll < 1 || unroll > 8) return fail("compact.unroll must be in [1,8]");
-  p->block = block; p->unroll = unroll; p->vec = vec;
-  p->tile_rows = (int64_t)block * vec * unroll;
-  if (p->tile_rows * 4 * (two ? 2 : 1) > 46 * 1024) return fail("compact tile of %lld rows does not fit static shared memory", (long long)p->tile_rows);
   const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)vec * 4);
+  if (!aligned) variant = 0;                       // bulk copies need 16-byte aligned columns
+  size_t row_bytes = 0;
+  for (const auto &u : spec.used) row_bytes += dtype_size(u.dtype);
+  if (variant == 0)
+    while (unroll > 1 && (int64_t)block * vec * unroll * 4 * (two ? 2 : 1) > 46 * 1024) unroll /= 2;   // static shared memory
+  else
+    while (unroll > 1 && 128 + (size_t)block * vec * unroll * (2 * row_bytes + 4 * (two ? 2 : 1)) > 200 * 1024) unroll /= 2;
+  p->block = block; p->unroll = unroll; p->vec = vec; p->variant = variant;
+  p->tile_rows = (int64_t)block * vec * unroll;
+  p->smem = variant == 1 ? 128 + (size_t)p->tile_rows * (2 * row_bytes + 4 * (two ? 2 : 1)) : 0;
+  if (variant == 0 && p->tile_rows * 4 * (two ? 2 : 1) > 46 * 1024) return fail("compact tile of %lld rows does not fit static shared memory", (long long)p->tile_rows);
   spec.defines = {{"WDB_VEC", vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("compact.ld_hint", 0)},
                   {"WDB_ST_HINT", 0}, {"WDB_BLOCK", block}, {"WDB_UNROLL", unroll}, {"WDB_NOUT", two ? 2 : 1},
-                  {"WDB_THRESH", two ? thresh : 0}, {"WDB_MIN_CTAS", opt("compact.min_ctas", 1)}, {"WDB_LB", opt("compact.lookback", 4)}};
+                  {"WDB_THRESH", two ? thresh : 0}, {"WDB_MIN_CTAS", opt("compact.min_ctas", 1)},
+                  {"WDB_LB", opt("compact.lookback", variant == 1 ? 4 : 1)}, {"WDB_BULK", variant == 1 ? 1 : 0}};
+  if (variant == 1) spec.defines.push_back({"WDB_TILE", p->tile_rows});
   spec.fns.push_back({"expr", "float", expr});
   if (two) spec.fns.push_back({"expr2", "float", expr2});
   spec.fns.push_back({"cond", "bool", cond});
@@ -54,7 +64,8 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
   const int block = p.block;
   const int64_t tile_rows = p.tile_rows;
   Kernel k;
-  if (get_kernel(d, gen_source(spec), "wdb_compact.cu", "wdb_compact", &k)) return 1;
+  const bool bulk = p.variant == 1;
+  if (get_kernel(d, gen_source(spec), "wdb_compact.cu", bulk ? "wdb_compact_bulk" : "wdb_compact", &k)) return 1;
 
   const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
   // scratch: [0,8) survivor count, [8,12) ticket, [64, 64+8*ntiles) tile status words
@@ -66,20 +77,25 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
   unsigned *d_ticket = (unsigned *)(sc + 8);
   unsigned long long *d_status = (unsigned long long *)(sc + 64);
   if (ntiles > 0) {
-    if (!k.max_ctas_per_sm) {
-      int nb = 0;
-      WDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)k.fn, block, 0));
-      k.max_ctas_per_sm = std::max(nb, 1);
-    }
-    int64_t per_sm = std::min<int64_t>(k.max_ctas_per_sm, opt("compact.ctas_per_sm", 8));
+    if (p.smem > 48 * 1024) WDB_CUDA(cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    int nb = 0;
+    WDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)k.fn, block, p.smem));
+    if (nb < 1) return fail("compaction kernel does not fit on an SM (%zu bytes of shared memory)", p.smem);
+    // the bulk variant assigns tiles statically: its grid must not exceed what is co-resident
+    int64_t per_sm = std::min<int64_t>(nb, opt("compact.ctas_per_sm", 8));
     unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)d->num_sms * per_sm);
     std::vector<const void *> ptrs;
     for (const auto &u : spec.used) ptrs.push_back(cols[u.table_index].dptr);
     if (ptrs.empty()) ptrs.push_back(nullptr);
     long long nn = n, nt = ntiles;
     long long cap = out_cap;
-    void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_ticket, &d_cnt, &nt, &tau, &cap};
-    if (launch(k, grid, block, 0, stream, args)) return 1;
+    if (bulk) {
+      void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_cnt, &nt, &tau, &cap};
+      if (launch(k, grid, block, p.smem, stream, args)) return 1;
+    } else {
+      void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_ticket, &d_cnt, &nt, &tau, &cap};
+      if (launch(k, grid, block, 0, stream, args)) return 1;
+    }
   }
   if (d_count) WDB_CUDA(cudaMemcpyAsync(d_count, d_cnt, 8, cudaMemcpyDeviceToDevice, stream));
   if (h_count) {

@@ -79,6 +79,14 @@ int get_device(int id, Device **out) {
       if (p.major != 10)
         return fail("warpcore targets Blackwell sm_100a (B200); device %d is sm_%d%d", id, p.major, p.minor);
       d->arch = "sm_" + std::to_string(p.major) + std::to_string(p.minor) + "a";
+      // scratch buffers come from the stream-ordered allocator; keep freed memory cached instead of
+      // returning it to the driver at every synchronisation (the default release threshold is 0)
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
       d->ready = true;
     }
   }
