@@ -58,8 +58,18 @@ def test_only_referenced_columns_are_loaded(tmp_path):
 
 
 def test_compact_kernel_uses_ballot_popc_and_lookback(tmp_path):
+    # default variant: TMA bulk-copy ring (UBLKCP + mbarrier), ballot/popc ranking, status-word look-back
     _, cubin = wc.debug_compile("compact", SCHEMA, "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", wc.COMPACT)
     sass = sass_of(cubin, tmp_path)
+    assert "wdb_compact_bulk" in sass and "UBLKCP" in sass and "SYNCS" in sass
+    assert "VOTE" in sass and "POPC" in sass and "LDG.E.64.STRONG.GPU" in sass
+    # ticket variant: register-staged vector loads, atomic tile ticket
+    wc.set_option("compact.variant", 0)
+    try:
+        _, cubin = wc.debug_compile("compact", SCHEMA, "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", wc.COMPACT)
+    finally:
+        wc.set_option("compact.variant", 1)
+    sass = sass_of(cubin, tmp_path, "k0.cubin")
     assert "VOTE" in sass and "POPC" in sass and "ATOMG" in sass and "LDG.E.64.STRONG.GPU" in sass
 
 

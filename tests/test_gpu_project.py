@@ -166,6 +166,22 @@ def test_kernel_variants_agree(variant, vec, unroll, block):
             wc.set_option(k, v)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_compaction_variants_agree(variant):
+    """ticket + register loads / TMA bulk ring / two-pass count-scan-scatter: identical packed output."""
+    n = 2_000_003
+    t = {"price": orc.synth_f32(n, 13, 0.0, 40.0), "quantity": orc.synth_i32(n, 14, 1, 101)}
+    d = dev(t)
+    try:
+        wc.set_option("compact.variant", variant)
+        for text, where in [("price * 0.9", "price > 20"), ("price * quantity", "quantity < 3"), ("price", "price > 39.9"), ("price", "price >= 0")]:
+            ref = orc.filter_compact(text, where, t)
+            out, cnt = ops.project_filter(d, orc.Expr(text).cuda(), orc.Expr(where).cuda(), wc.COMPACT)
+            assert cnt == len(ref) and np.array_equal(bits(out[:cnt].cpu().numpy()), bits(ref)), (variant, text, where)
+    finally:
+        wc.set_option("compact.variant", 1)
+
+
 def test_compile_error_and_recovery():
     # tests/jit_error_test.cpp:19-33
     d = dev({"price": np.array([1.0], np.float32), "quantity": np.array([1], np.int32)})

@@ -131,6 +131,11 @@ def sweep_compact(n):
             if rows < 2048 or 128 + rows * 12 > 200 * 1024 or minc * block > 2048:
                 continue
             cfgs.append({"variant": 1, "vec": vec, "unroll": unroll, "block": block, "min_ctas": minc, "lookback": lb, "ctas_per_sm": 8})
+        for vec, unroll, block in itertools.product([4, 8], [1, 2, 4], [128, 256, 512]):
+            if block * vec * unroll * 4 <= 46 * 1024:
+                cfgs.append({"variant": 2, "vec": vec, "unroll": unroll, "block": block, "min_ctas": 1, "lookback": 1, "ctas_per_sm": 8})
+        if os.environ.get("SWEEP_ONLY_VARIANT"):
+            cfgs = [c for c in cfgs if c["variant"] == int(os.environ["SWEEP_ONLY_VARIANT"])]
         for cfg in cfgs:
             for k, v in cfg.items():
                 wc.set_option("compact." + k, v)

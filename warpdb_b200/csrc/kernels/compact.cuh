@@ -81,7 +81,7 @@ __device__ __forceinline__ i64 wdb_lookback(const u64 *__restrict__ status, cons
   }
 }
 
-#if !WDB_BULK
+#if !WDB_BULK && !WDB_TWOPASS
 // ---- variant 0: register-staged vector loads, tiles handed out in ticket order
 extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
 wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n,
@@ -222,7 +222,7 @@ wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
   }
 }
 
-#endif  // !WDB_BULK
+#endif  // variant 0
 
 #if WDB_BULK
 // ---- variant 1: the same algorithm with the column tiles streamed into a double-buffered shared
@@ -389,5 +389,141 @@ wdb_compact_bulk(const wdb_cols C, float *__restrict__ out, float *__restrict__ 
       }
     // barrier (A) of the next iteration orders these reads before the next staging writes
   }
+}
+#endif
+
+#if WDB_TWOPASS
+// ---- variant 2: two streaming passes without any inter-CTA dependency.
+//   wdb_count    every warp counts the survivors of its chunk of WDB_WARP_ROWS rows (condition only)
+//   (host)       exclusive scan of the chunk counts
+//   wdb_scatter  every warp re-reads its chunk, ranks survivors with ballots, stages them in a
+//                warp-private slice of shared memory and writes them at its scanned offset
+// No tickets, no look-back, no block barriers: both kernels are plain streaming kernels.  The price
+// is reading the columns the condition needs a second time: (cond bytes) + (all used bytes) +
+// 4*NOUT*selectivity per row instead of (all used bytes) + 4*NOUT*selectivity.
+extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
+wdb_count(const wdb_cols C, const i64 n, u32 *__restrict__ counts, const i64 nchunks, const float wdb_tau) {
+  const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const i64 chunk = (i64)blockIdx.x * WDB_NWARPS + warp;
+  if (chunk >= nchunks) return;
+  const i64 row0 = chunk * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
+  u32 cnt = 0;
+  if ((chunk + 1) * WDB_WARP_ROWS <= n) {
+    wdb_rows R[WDB_UNROLL];
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows(C, row0 + (i64)u * WDB_SLAB_ROWS, R[u]);
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u)
+#pragma unroll
+      for (int j = 0; j < WDB_VEC; ++j) cnt += WDB_KEEP(R[u], j) ? 1u : 0u;
+  } else {
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u)
+      for (int j = 0; j < WDB_VEC; ++j) {
+        const i64 row = row0 + (i64)u * WDB_SLAB_ROWS + j;
+        if (row < n) {
+          wdb_rows T1;
+          wdb_load_row1(C, row, T1, 0);
+          cnt += WDB_KEEP(T1, 0) ? 1u : 0u;
+        }
+      }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(WDB_FULL_MASK, cnt, o);
+  if (lane == 0) counts[chunk] = cnt;
+}
+
+extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
+wdb_scatter(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n,
+            const i64 *__restrict__ offsets, const i64 nchunks, const float wdb_tau, const i64 out_cap) {
+  __shared__ float s_stage[WDB_NWARPS][WDB_WARP_ROWS];
+#if WDB_NOUT == 2
+  __shared__ float s_stage2[WDB_NWARPS][WDB_WARP_ROWS];
+#endif
+  const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const u32 lt = wdb_lanemask_lt();
+  const i64 chunk = (i64)blockIdx.x * WDB_NWARPS + warp;
+  if (chunk >= nchunks) return;
+  const i64 row0 = chunk * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
+  const i64 g0 = offsets[chunk];
+  u32 flags[WDB_UNROLL];
+  float vals[WDB_UNROLL][WDB_VEC];
+#if WDB_NOUT == 2
+  float vals2[WDB_UNROLL][WDB_VEC];
+#endif
+  if ((chunk + 1) * WDB_WARP_ROWS <= n) {
+    wdb_rows R[WDB_UNROLL];
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows(C, row0 + (i64)u * WDB_SLAB_ROWS, R[u]);
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) {
+      u32 m = 0;
+#pragma unroll
+      for (int j = 0; j < WDB_VEC; ++j) {
+        m |= (WDB_KEEP(R[u], j) ? 1u : 0u) << j;
+        vals[u][j] = WDB_EXPR(R[u], j);
+#if WDB_NOUT == 2
+        vals2[u][j] = WDB_EXPR2(R[u], j);
+#endif
+      }
+      flags[u] = m;
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) {
+      u32 m = 0;
+#pragma unroll
+      for (int j = 0; j < WDB_VEC; ++j) {
+        const i64 row = row0 + (i64)u * WDB_SLAB_ROWS + j;
+        vals[u][j] = 0.0f;
+#if WDB_NOUT == 2
+        vals2[u][j] = 0.0f;
+#endif
+        if (row < n) {
+          wdb_rows T1;
+          wdb_load_row1(C, row, T1, 0);
+          if (WDB_KEEP(T1, 0)) {
+            m |= 1u << j;
+            vals[u][j] = WDB_EXPR(T1, 0);
+#if WDB_NOUT == 2
+            vals2[u][j] = WDB_EXPR2(T1, 0);
+#endif
+          }
+        }
+      }
+      flags[u] = m;
+    }
+  }
+  u32 total = 0;
+#pragma unroll
+  for (int u = 0; u < WDB_UNROLL; ++u) {
+    u32 pre = 0, tot = 0;
+#pragma unroll
+    for (int j = 0; j < WDB_VEC; ++j) {
+      const u32 b = __ballot_sync(WDB_FULL_MASK, (flags[u] >> j) & 1u);
+      pre += __popc(b & lt);
+      tot += __popc(b);
+    }
+    u32 pos = total + pre;
+#pragma unroll
+    for (int j = 0; j < WDB_VEC; ++j)
+      if ((flags[u] >> j) & 1u) {
+        s_stage[warp][pos] = vals[u][j];
+#if WDB_NOUT == 2
+        s_stage2[warp][pos] = vals2[u][j];
+#endif
+        ++pos;
+      }
+    total += tot;
+  }
+  __syncwarp();
+  const int mis = (int)(g0 & 31);
+  for (int i = (int)lane - mis; i < (int)total; i += 32)
+    if (i >= 0 && g0 + i < out_cap) {
+      out[g0 + i] = s_stage[warp][i];
+#if WDB_NOUT == 2
+      out2[g0 + i] = s_stage2[warp][i];
+#endif
+    }
 }
 #endif

@@ -5,6 +5,61 @@
 
 namespace wdb {
 
+// ---- exclusive scan of u32 chunk counts into i64 offsets (two-pass compaction) -----------------
+constexpr int kScanBlock = 1024, kScanItems = 16;
+__global__ void __launch_bounds__(kScanBlock) scan_local_kernel(const unsigned *__restrict__ in, long long *__restrict__ out,
+                                                                long long *__restrict__ block_sums, long long m) {
+  __shared__ long long s_warp[kScanBlock / 32];
+  const long long base = ((long long)blockIdx.x * kScanBlock + threadIdx.x) * kScanItems;
+  unsigned v[kScanItems];
+  long long sum = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) { v[i] = base + i < m ? in[base + i] : 0u; sum += v[i]; }
+  long long incl = sum;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    long long w = s_warp[lane];
+    long long wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= (unsigned)o) wi += t; }
+    s_warp[lane] = wi - w;
+    if (lane == 31) block_sums[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  long long run = s_warp[warp] + incl - sum;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) { if (base + i < m) out[base + i] = run; run += v[i]; }
+}
+__global__ void __launch_bounds__(1024) scan_sums_kernel(long long *__restrict__ block_sums, long long nb, long long *__restrict__ total) {
+  // single block: exclusive scan of the block sums in place (nb is small: m / 16384)
+  __shared__ long long s_part[1024];
+  const long long per = (nb + 1023) / 1024;
+  const long long b = (long long)threadIdx.x * per, e = min(b + per, nb);
+  long long sum = 0;
+  for (long long i = b; i < e; ++i) sum += block_sums[i];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    for (int i = 0; i < 1024; ++i) { const long long t = s_part[i]; s_part[i] = run; run += t; }
+    *total = run;
+  }
+  __syncthreads();
+  long long run = s_part[threadIdx.x];
+  for (long long i = b; i < e; ++i) { const long long t = block_sums[i]; block_sums[i] = run; run += t; }
+}
+__global__ void __launch_bounds__(kScanBlock) scan_add_kernel(long long *__restrict__ out, const long long *__restrict__ block_sums, long long m) {
+  const long long base = ((long long)blockIdx.x * kScanBlock + threadIdx.x) * kScanItems;
+  const long long add = block_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i)
+    if (base + i < m) out[base + i] += add;
+}
+
 struct CompactPlan { GenSpec spec; int block, unroll, vec, variant; int64_t tile_rows; bool two; size_t smem; };
 
 static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, const char *expr2, const char *cond,
@@ -19,26 +74,26 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
     if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
   const int block = (int)opt("compact.block", 256), vec = (int)opt("compact.vec", 8);
   int unroll = (int)opt("compact.unroll", 4);
-  int variant = (int)opt("compact.variant", 1);   // 0 ticket + register loads, 1 TMA bulk ring
+  int variant = (int)opt("compact.variant", 1);   // 0 ticket + register loads, 1 TMA bulk ring, 2 two-pass count/scatter
   if (vec != 4 && vec != 8) return fail("compact.vec must be 4 or 8");
   if (block < 32 || block > 1024 || (block & 31)) return fail("compact.block must be a multiple of 32 in [32,1024]");
   if (unroll < 1 || unroll > 8) return fail("compact.unroll must be in [1,8]");
   const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)vec * 4);
-  if (!aligned) variant = 0;                       // bulk copies need 16-byte aligned columns
+  if (!aligned && variant == 1) variant = 0;       // bulk copies need 16-byte aligned columns
   size_t row_bytes = 0;
   for (const auto &u : spec.used) row_bytes += dtype_size(u.dtype);
-  if (variant == 0)
+  if (variant != 1)
     while (unroll > 1 && (int64_t)block * vec * unroll * 4 * (two ? 2 : 1) > 46 * 1024) unroll /= 2;   // static shared memory
   else
     while (unroll > 1 && 128 + (size_t)block * vec * unroll * (2 * row_bytes + 4 * (two ? 2 : 1)) > 200 * 1024) unroll /= 2;
   p->block = block; p->unroll = unroll; p->vec = vec; p->variant = variant;
   p->tile_rows = (int64_t)block * vec * unroll;
   p->smem = variant == 1 ? 128 + (size_t)p->tile_rows * (2 * row_bytes + 4 * (two ? 2 : 1)) : 0;
-  if (variant == 0 && p->tile_rows * 4 * (two ? 2 : 1) > 46 * 1024) return fail("compact tile of %lld rows does not fit static shared memory", (long long)p->tile_rows);
+  if (variant != 1 && p->tile_rows * 4 * (two ? 2 : 1) > 46 * 1024) return fail("compact tile of %lld rows does not fit static shared memory", (long long)p->tile_rows);
   spec.defines = {{"WDB_VEC", vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("compact.ld_hint", 0)},
                   {"WDB_ST_HINT", 0}, {"WDB_BLOCK", block}, {"WDB_UNROLL", unroll}, {"WDB_NOUT", two ? 2 : 1},
                   {"WDB_THRESH", two ? thresh : 0}, {"WDB_MIN_CTAS", opt("compact.min_ctas", 1)},
-                  {"WDB_LB", opt("compact.lookback", variant == 1 ? 4 : 1)}, {"WDB_BULK", variant == 1 ? 1 : 0}};
+                  {"WDB_LB", opt("compact.lookback", variant == 1 ? 4 : 1)}, {"WDB_BULK", variant == 1 ? 1 : 0}, {"WDB_TWOPASS", variant == 2 ? 1 : 0}};
   if (variant == 1) spec.defines.push_back({"WDB_TILE", p->tile_rows});
   spec.fns.push_back({"expr", "float", expr});
   if (two) spec.fns.push_back({"expr2", "float", expr2});
@@ -63,6 +118,51 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
   GenSpec &spec = p.spec;
   const int block = p.block;
   const int64_t tile_rows = p.tile_rows;
+  if (p.variant == 2) {  // two streaming passes: count per warp chunk, scan, scatter
+    const std::string src = gen_source(spec);
+    Kernel kc, ks;
+    if (get_kernel(d, src, "wdb_compact.cu", "wdb_count", &kc) || get_kernel(d, src, "wdb_compact.cu", "wdb_scatter", &ks)) return 1;
+    const int nwarps = block / 32;
+    const int64_t chunk_rows = tile_rows / nwarps;
+    const int64_t nchunks = (n + chunk_rows - 1) / chunk_rows;
+    const int64_t nsb = (nchunks + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems);
+    // scratch: [0,8) total, [64, ...) offsets i64[nchunks], block sums i64[nsb], counts u32[nchunks]
+    const size_t off_bytes = 8 * (size_t)std::max<int64_t>(nchunks, 1), sum_bytes = 8 * (size_t)std::max<int64_t>(nsb, 1);
+    const size_t need = 64 + off_bytes + sum_bytes + 4 * (size_t)std::max<int64_t>(nchunks, 1);
+    if (ensure_scratch(d, need)) return 1;
+    char *sc = (char *)d->scratch;
+    long long *d_total = (long long *)sc;
+    long long *d_offs = (long long *)(sc + 64);
+    long long *d_sums = (long long *)(sc + 64 + off_bytes);
+    unsigned *d_counts = (unsigned *)(sc + 64 + off_bytes + sum_bytes);
+    WDB_CUDA(cudaMemsetAsync(sc, 0, 64, stream));
+    if (nchunks > 0) {
+      std::vector<const void *> ptrs;
+      for (const auto &u : spec.used) ptrs.push_back(cols[u.table_index].dptr);
+      if (ptrs.empty()) ptrs.push_back(nullptr);
+      long long nn = n, nc = nchunks, cap = out_cap;
+      const unsigned grid = (unsigned)((nchunks + nwarps - 1) / nwarps);
+      {
+        void *args[] = {ptrs.data(), &nn, &d_counts, &nc, &tau};
+        if (launch(kc, grid, block, 0, stream, args)) return 1;
+      }
+      scan_local_kernel<<<(unsigned)nsb, kScanBlock, 0, stream>>>(d_counts, d_offs, d_sums, nchunks);
+      scan_sums_kernel<<<1, 1024, 0, stream>>>(d_sums, nsb, d_total);
+      scan_add_kernel<<<(unsigned)nsb, kScanBlock, 0, stream>>>(d_offs, d_sums, nchunks);
+      stats().launches += 3;
+      WDB_CUDA(cudaGetLastError());
+      {
+        void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_offs, &nc, &tau, &cap};
+        if (launch(ks, grid, block, 0, stream, args)) return 1;
+      }
+    }
+    if (d_count) WDB_CUDA(cudaMemcpyAsync(d_count, d_total, 8, cudaMemcpyDeviceToDevice, stream));
+    if (h_count) {
+      WDB_CUDA(cudaMemcpyAsync(h_count, d_total, 8, cudaMemcpyDeviceToHost, stream));
+      WDB_CUDA(cudaStreamSynchronize(stream));
+    }
+    return 0;
+  }
   Kernel k;
   const bool bulk = p.variant == 1;
   if (get_kernel(d, gen_source(spec), "wdb_compact.cu", bulk ? "wdb_compact_bulk" : "wdb_compact", &k)) return 1;

@@ -29,7 +29,7 @@ static int plan_topk(const wdb_col_t *cols, int ncols, const char *key, const ch
   spec.used = find_used_columns(cols, ncols, {key, val, has_cond ? cond : ""});
   for (const auto &u : spec.used)
     if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
-  p->block = (int)opt("topk.block", 256);
+  p->block = (int)opt("topk.block", 512);   // profiles/r01_sweep_topk_2e9.jsonl
   p->unroll = (int)opt("topk.unroll", 2);
   p->vec = (int)opt("topk.vec", 8);
   p->K = K;
