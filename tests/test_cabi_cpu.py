@@ -57,20 +57,25 @@ def test_only_referenced_columns_are_loaded(tmp_path):
     assert "#define WDB_NUSED 1" in src and "quantity" not in src.split("---- end UDF ----")[1]
 
 
-def test_compact_kernel_uses_ballot_popc_and_lookback(tmp_path):
-    # default variant: TMA bulk-copy ring (UBLKCP + mbarrier), ballot/popc ranking, status-word look-back
+def test_compact_kernels(tmp_path):
+    # default: two streaming passes (count -> scan -> scatter), ballot/popc ranking, no atomics, no barriers
     _, cubin = wc.debug_compile("compact", SCHEMA, "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", wc.COMPACT)
     sass = sass_of(cubin, tmp_path)
-    assert "wdb_compact_bulk" in sass and "UBLKCP" in sass and "SYNCS" in sass
-    assert "VOTE" in sass and "POPC" in sass and "LDG.E.64.STRONG.GPU" in sass
-    # ticket variant: register-staged vector loads, atomic tile ticket
-    wc.set_option("compact.variant", 0)
+    assert "wdb_count" in sass and "wdb_scatter" in sass and "VOTE" in sass and "POPC" in sass
+    assert "ATOMG" not in sass and "BAR.SYNC" not in sass and re.search(r"LDG\.E\.NA\.\w+\.256", sass)
     try:
-        _, cubin = wc.debug_compile("compact", SCHEMA, "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", wc.COMPACT)
-    finally:
+        # single pass, TMA bulk-copy ring (UBLKCP + mbarrier), status-word look-back
         wc.set_option("compact.variant", 1)
-    sass = sass_of(cubin, tmp_path, "k0.cubin")
-    assert "VOTE" in sass and "POPC" in sass and "ATOMG" in sass and "LDG.E.64.STRONG.GPU" in sass
+        _, cubin = wc.debug_compile("compact", SCHEMA, "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", wc.COMPACT)
+        sass = sass_of(cubin, tmp_path, "k1.cubin")
+        assert "wdb_compact_bulk" in sass and "UBLKCP" in sass and "SYNCS" in sass and "LDG.E.64.STRONG.GPU" in sass
+        # single pass, register-staged vector loads, atomic tile ticket
+        wc.set_option("compact.variant", 0)
+        _, cubin = wc.debug_compile("compact", SCHEMA, "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", wc.COMPACT)
+        sass = sass_of(cubin, tmp_path, "k0.cubin")
+        assert "VOTE" in sass and "POPC" in sass and "ATOMG" in sass and "LDG.E.64.STRONG.GPU" in sass
+    finally:
+        wc.set_option("compact.variant", 2)
 
 
 def test_bulk_variant_emits_tma_bulk_copies(tmp_path):

@@ -179,7 +179,7 @@ def test_compaction_variants_agree(variant):
             out, cnt = ops.project_filter(d, orc.Expr(text).cuda(), orc.Expr(where).cuda(), wc.COMPACT)
             assert cnt == len(ref) and np.array_equal(bits(out[:cnt].cpu().numpy()), bits(ref)), (variant, text, where)
     finally:
-        wc.set_option("compact.variant", 1)
+        wc.set_option("compact.variant", 2)
 
 
 def test_compile_error_and_recovery():

@@ -15,8 +15,13 @@ def ev():
 for G in (1000, 10_000_000):
     qty = ops.synth_i32(n, 0xC0FFEE + 104, 0, G)
     table = {"price": price, "quantity": qty}
-    for cfg in ({}, {"group.smem_slots": 0}, {"group.vec": 8, "group.unroll": 2}, {"group.smem_slots": 0, "group.vec": 8}):
-        for k, v in {"group.smem_slots": -1, "group.vec": 4, "group.unroll": 2}.items():
+    cfgs = [{}, {"group.wp_slots": 0}, {"group.wp_slots": 0, "group.smem_slots": 0}]
+    if G <= 2000:
+        cfgs += [{"group.wp_slots": 4096}, {"group.wp_unroll": 2}, {"group.wp_unroll": 2, "group.wp_vec": 4}, {"group.wp_warps": 4},
+                 {"group.wp_unroll": 8, "group.wp_vec": 4}]
+    for cfg in cfgs:
+        for k, v in {"group.smem_slots": -1, "group.vec": 4, "group.unroll": 2, "group.wp_slots": -1, "group.wp_unroll": 4, "group.wp_vec": 8,
+                     "group.wp_warps": 8}.items():
             wc.set_option(k, v)
         for k, v in cfg.items():
             wc.set_option(k, v)

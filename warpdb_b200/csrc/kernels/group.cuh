@@ -132,3 +132,132 @@ wdb_group(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T) 
   }
 #endif
 }
+
+#if WDB_WP_SLOTS > 0
+// ---- small-cardinality kernel: warp-private shared-memory tables, no shared-memory atomics on
+// the accumulation path.  sm_100 has no native 64-bit (or floating-point) shared-memory atomic:
+// atomicAdd(double*) on shared memory is a CAS loop on the single ATOMS pipe, which caps the
+// kernel above at ~0.3 rows/clk/SM.  Here every warp owns a private open-addressing table
+// (WDB_WP_SLOTS slots of key + fp64 sum [+ u32 count]); the lanes of a warp that hit the same slot
+// in the same step are found with MATCH.ANY, their values are combined with shuffles, and the
+// lowest lane does a plain LDS/DADD/STS read-modify-write.  A 32-bit CAS is used only to claim an
+// empty slot (once per distinct key per warp).  Tables are folded into the global table at the end.
+#define WDB_WP_WARPS (WDB_BLOCK / 32)
+struct wdb_wp_table {
+  int *keys;
+  double *sums;
+  u32 *cnts;
+};
+__device__ __forceinline__ void wdb_wp_row(const wdb_table &T, const wdb_wp_table &W, const bool valid, const int key,
+                                           const float val, const i64 row, const u32 lane) {
+  // 1. slot of this lane's key in the warp's table
+  u32 h = 0xffffffffu - lane;            // distinct per lane: lanes without a row match nobody
+  bool in_table = false;
+  if (valid && key != WDB_KEY_EMPTY) {
+    u32 s = wdb_hash32(key) >> (32 - WDB_WP_LOG2);
+#pragma unroll 1
+    for (int p = 0; p < WDB_WP_PROBES; ++p) {
+      const int k = W.keys[s];
+      if (k == key) { in_table = true; break; }
+      if (k == WDB_KEY_EMPTY) {
+        const int prev = atomicCAS(&W.keys[s], WDB_KEY_EMPTY, key);
+        if (prev == WDB_KEY_EMPTY || prev == key) { in_table = true; break; }
+      }
+      s = (s + 1u) & (WDB_WP_SLOTS - 1u);
+    }
+    if (in_table) h = s;
+  }
+  // 2. lanes sharing a slot combine their contributions; the lowest lane applies them
+  const u32 peers = __match_any_sync(WDB_FULL_MASK, h);
+  double acc = (double)val;
+  u32 rem = peers & ~(1u << lane);
+  while (__any_sync(WDB_FULL_MASK, rem != 0u)) {
+    const int src = rem ? (__ffs((int)rem) - 1) : (int)lane;
+    const double o = __shfl_sync(WDB_FULL_MASK, (double)val, src);
+    if (rem) { acc += o; rem &= rem - 1u; }
+  }
+  if (in_table) {
+    if ((u32)(__ffs((int)peers) - 1) == lane) {
+      if (WDB_NEEDS & WDB_NEED_SUM_BIT) W.sums[h] += acc;
+      if (WDB_NEEDS & WDB_NEED_CNT_BIT) W.cnts[h] += (u32)__popc(peers);
+    }
+  } else if (valid) {  // table full or sentinel key: straight to the global table
+    const i64 g = wdb_table_slot(T, key);
+    if (g >= 0) wdb_table_add<WDB_NEEDS>(T, g, (double)val, 1ull, 0, 0, row);
+  }
+  __syncwarp();
+}
+
+extern "C" __global__ void __launch_bounds__(WDB_BLOCK, 1)
+wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T) {
+  extern __shared__ __align__(16) unsigned char wdb_smem[];
+  const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  double *all_sums = reinterpret_cast<double *>(wdb_smem);
+  int *all_keys = reinterpret_cast<int *>(wdb_smem + sizeof(double) * WDB_WP_SLOTS * WDB_WP_WARPS);
+  u32 *all_cnts = reinterpret_cast<u32 *>(wdb_smem + (sizeof(double) + sizeof(int)) * WDB_WP_SLOTS * WDB_WP_WARPS);
+  for (int s = threadIdx.x; s < WDB_WP_SLOTS * WDB_WP_WARPS; s += WDB_BLOCK) {
+    all_keys[s] = WDB_KEY_EMPTY;
+    all_sums[s] = 0.0;
+    if (WDB_NEEDS & WDB_NEED_CNT_BIT) all_cnts[s] = 0u;
+  }
+  __syncthreads();
+  wdb_wp_table W;
+  W.keys = all_keys + warp * WDB_WP_SLOTS;
+  W.sums = all_sums + warp * WDB_WP_SLOTS;
+  W.cnts = all_cnts + warp * WDB_WP_SLOTS;
+
+  const i64 nvec = n / WDB_VEC;
+  const i64 tile_vecs = (i64)WDB_BLOCK * WDB_UNROLL;
+  const i64 ntiles = (nvec + tile_vecs - 1) / tile_vecs;
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const i64 v0 = tile * tile_vecs + threadIdx.x;
+    wdb_rows R[WDB_UNROLL];
+    const bool full = (tile + 1) * tile_vecs <= nvec;
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u)
+      if (full || v0 + (i64)u * WDB_BLOCK < nvec) wdb_load_rows(C, (v0 + (i64)u * WDB_BLOCK) * WDB_VEC, R[u]);
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) {
+      const bool have = full || v0 + (i64)u * WDB_BLOCK < nvec;     // warp-uniform except in the last tile
+      const i64 row = (v0 + (i64)u * WDB_BLOCK) * WDB_VEC;
+#pragma unroll
+      for (int j = 0; j < WDB_VEC; ++j) {
+        bool valid = have;
+        int key = 0;
+        float val = 0.0f;
+        if (have) {
+#if WDB_HAS_COND
+          valid = WDB_COND(R[u], j);
+#endif
+          key = WDB_KEY(R[u], j);
+          val = WDB_VAL(R[u], j);
+        }
+        wdb_wp_row(T, W, valid, key, val, row_base + row + j, lane);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {  // ragged tail: one row per thread of CTA 0
+    const i64 row = nvec * WDB_VEC + threadIdx.x;
+    bool valid = row < n;
+    int key = 0;
+    float val = 0.0f;
+    if (valid) {
+      wdb_rows R;
+      wdb_load_row1(C, row, R, 0);
+#if WDB_HAS_COND
+      valid = WDB_COND(R, 0);
+#endif
+      key = WDB_KEY(R, 0);
+      val = WDB_VAL(R, 0);
+    }
+    wdb_wp_row(T, W, valid, key, val, row_base + row, lane);
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < WDB_WP_SLOTS * WDB_WP_WARPS; s += WDB_BLOCK) {
+    const int key = all_keys[s];
+    if (key == WDB_KEY_EMPTY) continue;
+    const i64 g = wdb_table_slot(T, key);
+    if (g >= 0) wdb_table_add<WDB_NEEDS>(T, g, all_sums[s], (WDB_NEEDS & WDB_NEED_CNT_BIT) ? (u64)all_cnts[s] : 0ull, 0, 0, 0);
+  }
+}
+#endif

@@ -74,12 +74,12 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
     if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
   const int block = (int)opt("compact.block", 256), vec = (int)opt("compact.vec", 8);
   int unroll = (int)opt("compact.unroll", 4);
-  int variant = (int)opt("compact.variant", 1);   // 0 ticket + register loads, 1 TMA bulk ring, 2 two-pass count/scatter
+  int variant = (int)opt("compact.variant", 2);   // default from profiles/r01_sweep_compact_*.jsonl   // 0 ticket + register loads, 1 TMA bulk ring, 2 two-pass count/scatter
   if (vec != 4 && vec != 8) return fail("compact.vec must be 4 or 8");
   if (block < 32 || block > 1024 || (block & 31)) return fail("compact.block must be a multiple of 32 in [32,1024]");
   if (unroll < 1 || unroll > 8) return fail("compact.unroll must be in [1,8]");
   const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)vec * 4);
-  if (!aligned && variant == 1) variant = 0;       // bulk copies need 16-byte aligned columns
+  if (!aligned && variant == 1) variant = 2;       // bulk copies need 16-byte aligned columns
   size_t row_bytes = 0;
   for (const auto &u : spec.used) row_bytes += dtype_size(u.dtype);
   if (variant != 1)

@@ -117,7 +117,7 @@ static unsigned grid_for(Device *d, long long n) {
   return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)d->num_sms * 16));
 }
 
-struct GroupPlan { GenSpec spec; int block, unroll, vec, smem_slots; size_t smem_bytes; };
+struct GroupPlan { GenSpec spec; int block, unroll, vec, smem_slots, wp_slots; size_t smem_bytes; const char *entry; };
 
 static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const char *key, const char *cond, int needs,
                       int64_t cap_hint, bool check_alignment, GroupPlan *p) {
@@ -131,20 +131,46 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   p->unroll = (int)opt("group.unroll", 2);
   p->vec = (int)opt("group.vec", 4);
   if (p->vec != 4 && p->vec != 8) return fail("group.vec must be 4 or 8");
-  // shared pre-aggregation pays when the distinct keys fit the shared table; beyond that every row
-  // misses it and the probes are wasted work
+  // Small cardinalities (and SUM/COUNT/AVG): warp-private tables without shared-memory atomics.
+  // Otherwise shared pre-aggregation with atomics pays while the distinct keys fit the CTA's table;
+  // beyond that every row misses it and the probes are wasted work.
+  const int64_t expected = cap_hint / 2;                     // cap_hint = table capacity = 2 x expected groups
+  int64_t wp = opt("group.wp_slots", -1);
+  const bool wp_ok = (needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0;
+  if (wp < 0) wp = (wp_ok && expected <= 2200) ? (expected <= 550 ? 1024 : (expected <= 1100 ? 2048 : 4096)) : 0;
+  if (!wp_ok) wp = 0;
+  if (wp & (wp - 1)) return fail("group.wp_slots must be a power of two");
   int64_t slots = opt("group.smem_slots", -1);
-  if (slots < 0) slots = (cap_hint / 2 <= 2048) ? 4096 : 0;   // cap_hint = table capacity = 2 x expected groups
+  if (slots < 0) slots = (expected <= 2048) ? 4096 : 0;
   if (slots & (slots - 1)) return fail("group.smem_slots must be a power of two");
+  if (wp > 0) {
+    slots = 0;
+    const size_t per_slot = 8 + 4 + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0);
+    int warps = (int)std::min<int64_t>(opt("group.wp_warps", 8), (int64_t)(200 * 1024 / (per_slot * wp)));
+    if (warps < 1) return fail("group.wp_slots too large for shared memory");
+    p->block = 32 * warps;
+    p->unroll = (int)opt("group.wp_unroll", 4);
+    p->vec = (int)opt("group.wp_vec", 8);
+    p->smem_bytes = per_slot * (size_t)wp * warps;
+    p->entry = "wdb_group_wp";
+  } else {
+    p->entry = "wdb_group";
+  }
+  p->wp_slots = (int)wp;
   p->smem_slots = (int)slots;
   int log2 = 0;
   while ((1ll << log2) < slots) ++log2;
-  size_t per_slot = 8 + 4 + 4 + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) + ((needs & WDB_NEED_FIRST_BIT) ? 8 : 0);
-  p->smem_bytes = per_slot * (size_t)slots;
+  int wplog2 = 0;
+  while ((1ll << wplog2) < wp) ++wplog2;
+  if (wp == 0) {
+    size_t per_slot = 8 + 4 + 4 + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) + ((needs & WDB_NEED_FIRST_BIT) ? 8 : 0);
+    p->smem_bytes = per_slot * (size_t)slots;
+  }
   const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)p->vec * 4);
   spec.defines = {{"WDB_VEC", p->vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("group.ld_hint", 0)}, {"WDB_ST_HINT", 0},
                   {"WDB_BLOCK", p->block}, {"WDB_UNROLL", p->unroll}, {"WDB_NEEDS", needs}, {"WDB_SMEM_SLOTS", slots},
-                  {"WDB_SMEM_LOG2", log2}, {"WDB_SMEM_PROBES", opt("group.smem_probes", 4)}, {"WDB_HAS_COND", has_cond ? 1 : 0}};
+                  {"WDB_SMEM_LOG2", log2}, {"WDB_SMEM_PROBES", opt("group.smem_probes", 4)}, {"WDB_HAS_COND", has_cond ? 1 : 0},
+                  {"WDB_WP_SLOTS", wp}, {"WDB_WP_LOG2", wplog2}, {"WDB_WP_PROBES", opt("group.wp_probes", 16)}};
   spec.fns.push_back({"val", "float", (needs & ~WDB_NEED_CNT_BIT & ~WDB_NEED_FIRST_BIT) ? val : "0.0f"});  // COUNT never evaluates its argument (src/warpdb.cpp:376)
   spec.fns.push_back({"key", "int", key});
   if (has_cond) spec.fns.push_back({"cond", "bool", cond});
@@ -223,7 +249,7 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   GroupPlan p;
   if (plan_group(cols, ncols, val_expr, key_expr, cond, t->needs, t->cap, true, &p)) return 1;
   Kernel k;
-  if (get_kernel(d, gen_source(p.spec), "wdb_group.cu", "wdb_group", &k)) return 1;
+  if (get_kernel(d, gen_source(p.spec), "wdb_group.cu", p.entry, &k)) return 1;
   if (n == 0) return 0;
   if (p.smem_bytes > 48 * 1024) WDB_CUDA(cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
   int nb = 0;
