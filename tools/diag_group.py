@@ -15,13 +15,16 @@ def ev():
 for G in (1000, 10_000_000):
     qty = ops.synth_i32(n, 0xC0FFEE + 104, 0, G)
     table = {"price": price, "quantity": qty}
-    cfgs = [{}, {"group.wp_slots": 0}, {"group.wp_slots": 0, "group.smem_slots": 0}]
+    cfgs = [{}]
     if G <= 2000:
-        cfgs += [{"group.wp_slots": 4096}, {"group.wp_unroll": 2}, {"group.wp_unroll": 2, "group.wp_vec": 4}, {"group.wp_warps": 4},
-                 {"group.wp_unroll": 8, "group.wp_vec": 4}]
+        cfgs += [{"group.smem_slots": sl, "group.block": b, "group.unroll": u, "group.vec": v}
+                 for sl in (2048, 4096) for b in (256, 512) for u, v in ((2, 4), (4, 4), (2, 8))]
+        cfgs += [{"group.wp_slots": 2048}]
+    else:
+        cfgs += [{"group.block": 512}, {"group.unroll": 4}, {"group.vec": 8, "group.unroll": 2}]
     for cfg in cfgs:
-        for k, v in {"group.smem_slots": -1, "group.vec": 4, "group.unroll": 2, "group.wp_slots": -1, "group.wp_unroll": 4, "group.wp_vec": 8,
-                     "group.wp_warps": 8}.items():
+        for k, v in {"group.smem_slots": -1, "group.vec": 4, "group.unroll": 2, "group.block": 256, "group.wp_slots": -1, "group.wp_unroll": 4,
+                     "group.wp_vec": 8, "group.wp_warps": 8}.items():
             wc.set_option(k, v)
         for k, v in cfg.items():
             wc.set_option(k, v)

@@ -32,7 +32,7 @@ __device__ __forceinline__ wdb_smem_table wdb_smem_carve(unsigned char *base) {
   S.maxs = reinterpret_cast<i64 *>(base + off); off += (WDB_NEEDS & WDB_NEED_MINMAX_BIT) ? sizeof(i64) * WDB_SMEM_SLOTS : 0;
   S.first = reinterpret_cast<i64 *>(base + off); off += (WDB_NEEDS & WDB_NEED_FIRST_BIT) ? sizeof(i64) * WDB_SMEM_SLOTS : 0;
   S.keys = reinterpret_cast<int *>(base + off); off += sizeof(int) * WDB_SMEM_SLOTS;
-  S.cnts = reinterpret_cast<u32 *>(base + off);
+  S.cnts = reinterpret_cast<u32 *>(base + off);   // present only when counts are needed
   return S;
 }
 #endif
@@ -77,7 +77,7 @@ wdb_group(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T) 
   for (int s = threadIdx.x; s < WDB_SMEM_SLOTS; s += WDB_BLOCK) {
     S.keys[s] = WDB_KEY_EMPTY;
     S.sums[s] = 0.0;
-    S.cnts[s] = 0u;
+    if (WDB_NEEDS & WDB_NEED_CNT_BIT) S.cnts[s] = 0u;
     if (WDB_NEEDS & WDB_NEED_MINMAX_BIT) { S.mins[s] = WDB_ENC_PLUS_INF; S.maxs[s] = WDB_ENC_MINUS_INF; }
     if (WDB_NEEDS & WDB_NEED_FIRST_BIT) S.first[s] = 0x7fffffffffffffffll;
   }
@@ -127,7 +127,7 @@ wdb_group(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T) 
     if (key == WDB_KEY_EMPTY) continue;
     const i64 g = wdb_table_slot(T, key);
     if (g >= 0)
-      wdb_table_add<WDB_NEEDS>(T, g, S.sums[s], (u64)S.cnts[s], (WDB_NEEDS & WDB_NEED_MINMAX_BIT) ? S.mins[s] : 0,
+      wdb_table_add<WDB_NEEDS>(T, g, S.sums[s], (WDB_NEEDS & WDB_NEED_CNT_BIT) ? (u64)S.cnts[s] : 0ull, (WDB_NEEDS & WDB_NEED_MINMAX_BIT) ? S.mins[s] : 0,
                                (WDB_NEEDS & WDB_NEED_MINMAX_BIT) ? S.maxs[s] : 0, (WDB_NEEDS & WDB_NEED_FIRST_BIT) ? S.first[s] : 0);
   }
 #endif
@@ -139,19 +139,20 @@ wdb_group(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T) 
 // atomicAdd(double*) on shared memory is a CAS loop on the single ATOMS pipe, which caps the
 // kernel above at ~0.3 rows/clk/SM.  Here every warp owns a private open-addressing table
 // (WDB_WP_SLOTS slots of key + fp64 sum [+ u32 count]); the lanes of a warp that hit the same slot
-// in the same step are found with MATCH.ANY, their values are combined with shuffles, and the
-// lowest lane does a plain LDS/DADD/STS read-modify-write.  A 32-bit CAS is used only to claim an
+// in the same step arbitrate through a one-byte tag per slot, and the winner does a plain
+// LDS/DADD/STS read-modify-write.  A 32-bit CAS is used only to claim an
 // empty slot (once per distinct key per warp).  Tables are folded into the global table at the end.
 #define WDB_WP_WARPS (WDB_BLOCK / 32)
 struct wdb_wp_table {
   int *keys;
   double *sums;
   u32 *cnts;
+  unsigned char *tags;
 };
-__device__ __forceinline__ void wdb_wp_row(const wdb_table &T, const wdb_wp_table &W, const bool valid, const int key,
+__device__ __noinline__ void wdb_wp_row(const wdb_table &T, const wdb_wp_table &W, const bool valid, const int key,
                                            const float val, const i64 row, const u32 lane) {
   // 1. slot of this lane's key in the warp's table
-  u32 h = 0xffffffffu - lane;            // distinct per lane: lanes without a row match nobody
+  u32 h = 0;
   bool in_table = false;
   if (valid && key != WDB_KEY_EMPTY) {
     u32 s = wdb_hash32(key) >> (32 - WDB_WP_LOG2);
@@ -167,21 +168,22 @@ __device__ __forceinline__ void wdb_wp_row(const wdb_table &T, const wdb_wp_tabl
     }
     if (in_table) h = s;
   }
-  // 2. lanes sharing a slot combine their contributions; the lowest lane applies them
-  const u32 peers = __match_any_sync(WDB_FULL_MASK, h);
-  double acc = (double)val;
-  u32 rem = peers & ~(1u << lane);
-  while (__any_sync(WDB_FULL_MASK, rem != 0u)) {
-    const int src = rem ? (__ffs((int)rem) - 1) : (int)lane;
-    const double o = __shfl_sync(WDB_FULL_MASK, (double)val, src);
-    if (rem) { acc += o; rem &= rem - 1u; }
-  }
-  if (in_table) {
-    if ((u32)(__ffs((int)peers) - 1) == lane) {
-      if (WDB_NEEDS & WDB_NEED_SUM_BIT) W.sums[h] += acc;
-      if (WDB_NEEDS & WDB_NEED_CNT_BIT) W.cnts[h] += (u32)__popc(peers);
+  // 2. conflict-free accumulate: lanes that hit the same slot in this step arbitrate through a
+  // one-byte tag per slot (write lane id, re-read, the lane that reads back its own id owns the slot
+  // for this round); losers go round again.  (MATCH.ANY would find the peers in one instruction
+  // but measured ~400 cycles per warp instruction on B200.)
+  bool pending = in_table;
+  while (__any_sync(WDB_FULL_MASK, pending)) {
+    if (pending) W.tags[h] = (unsigned char)lane;
+    __syncwarp();
+    if (pending && W.tags[h] == (unsigned char)lane) {
+      if (WDB_NEEDS & WDB_NEED_SUM_BIT) W.sums[h] += (double)val;
+      if (WDB_NEEDS & WDB_NEED_CNT_BIT) W.cnts[h] += 1u;
+      pending = false;
     }
-  } else if (valid) {  // table full or sentinel key: straight to the global table
+    __syncwarp();
+  }
+  if (!in_table && valid) {  // table full or sentinel key: straight to the global table
     const i64 g = wdb_table_slot(T, key);
     if (g >= 0) wdb_table_add<WDB_NEEDS>(T, g, (double)val, 1ull, 0, 0, row);
   }
@@ -194,7 +196,8 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
   const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   double *all_sums = reinterpret_cast<double *>(wdb_smem);
   int *all_keys = reinterpret_cast<int *>(wdb_smem + sizeof(double) * WDB_WP_SLOTS * WDB_WP_WARPS);
-  u32 *all_cnts = reinterpret_cast<u32 *>(wdb_smem + (sizeof(double) + sizeof(int)) * WDB_WP_SLOTS * WDB_WP_WARPS);
+  unsigned char *all_tags = wdb_smem + (sizeof(double) + sizeof(int)) * WDB_WP_SLOTS * WDB_WP_WARPS;
+  u32 *all_cnts = reinterpret_cast<u32 *>(wdb_smem + (sizeof(double) + sizeof(int) + 1) * WDB_WP_SLOTS * WDB_WP_WARPS);
   for (int s = threadIdx.x; s < WDB_WP_SLOTS * WDB_WP_WARPS; s += WDB_BLOCK) {
     all_keys[s] = WDB_KEY_EMPTY;
     all_sums[s] = 0.0;
@@ -205,6 +208,7 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
   W.keys = all_keys + warp * WDB_WP_SLOTS;
   W.sums = all_sums + warp * WDB_WP_SLOTS;
   W.cnts = all_cnts + warp * WDB_WP_SLOTS;
+  W.tags = all_tags + warp * WDB_WP_SLOTS;
 
   const i64 nvec = n / WDB_VEC;
   const i64 tile_vecs = (i64)WDB_BLOCK * WDB_UNROLL;

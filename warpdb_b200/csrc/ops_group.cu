@@ -137,15 +137,18 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   const int64_t expected = cap_hint / 2;                     // cap_hint = table capacity = 2 x expected groups
   int64_t wp = opt("group.wp_slots", -1);
   const bool wp_ok = (needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0;
-  if (wp < 0) wp = (wp_ok && expected <= 2200) ? (expected <= 550 ? 1024 : (expected <= 1100 ? 2048 : 4096)) : 0;
+  if (wp < 0) wp = 0;   // measured 3-4x slower than the atomic path on B200 (profiles/r01_diag_group_*.jsonl); opt-in only
   if (!wp_ok) wp = 0;
   if (wp & (wp - 1)) return fail("group.wp_slots must be a power of two");
   int64_t slots = opt("group.smem_slots", -1);
-  if (slots < 0) slots = (expected <= 2048) ? 4096 : 0;
+  if (slots < 0) {   // load factor <= 0.5; a smaller table means more CTAs per SM to hide the shared-memory latency
+    slots = 0;
+    if (expected <= 2048) { slots = 1024; while (slots < 2 * expected) slots <<= 1; }
+  }
   if (slots & (slots - 1)) return fail("group.smem_slots must be a power of two");
   if (wp > 0) {
     slots = 0;
-    const size_t per_slot = 8 + 4 + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0);
+    const size_t per_slot = 8 + 4 + 1 + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0);
     int warps = (int)std::min<int64_t>(opt("group.wp_warps", 8), (int64_t)(200 * 1024 / (per_slot * wp)));
     if (warps < 1) return fail("group.wp_slots too large for shared memory");
     p->block = 32 * warps;
@@ -163,7 +166,7 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   int wplog2 = 0;
   while ((1ll << wplog2) < wp) ++wplog2;
   if (wp == 0) {
-    size_t per_slot = 8 + 4 + 4 + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) + ((needs & WDB_NEED_FIRST_BIT) ? 8 : 0);
+    size_t per_slot = 8 + 4 + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0) + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) + ((needs & WDB_NEED_FIRST_BIT) ? 8 : 0);
     p->smem_bytes = per_slot * (size_t)slots;
   }
   const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)p->vec * 4);
