@@ -127,7 +127,7 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   spec.used = find_used_columns(cols, ncols, {val, key, has_cond ? cond : ""});
   for (const auto &u : spec.used)
     if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
-  p->block = (int)opt("group.block", 256);
+  p->block = (int)opt("group.block", 512);   // profiles/r01_diag_group_tuning_1e9.jsonl
   p->unroll = (int)opt("group.unroll", 2);
   p->vec = (int)opt("group.vec", 4);
   if (p->vec != 4 && p->vec != 8) return fail("group.vec must be 4 or 8");
@@ -141,9 +141,9 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   if (!wp_ok) wp = 0;
   if (wp & (wp - 1)) return fail("group.wp_slots must be a power of two");
   int64_t slots = opt("group.smem_slots", -1);
-  if (slots < 0) {   // load factor <= 0.5; a smaller table means more CTAs per SM to hide the shared-memory latency
+  if (slots < 0) {
     slots = 0;
-    if (expected <= 2048) { slots = 1024; while (slots < 2 * expected) slots <<= 1; }
+    if (expected <= 2048) { slots = 1024; while (slots < 4 * expected) slots <<= 1; }   // load factor <= 0.25: short probe chains
   }
   if (slots & (slots - 1)) return fail("group.smem_slots must be a power of two");
   if (wp > 0) {
