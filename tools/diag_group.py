@@ -12,19 +12,20 @@ price = ops.synth_f32(n, 0xC0FFEE + 4, 0.0, 100.0)
 def ev():
     return torch.cuda.Event(enable_timing=True)
 
-for G in (1000, 10_000_000):
+for G in ((1000, 10_000_000) if len(sys.argv) < 3 else tuple(int(float(x)) for x in sys.argv[2].split(","))):
     qty = ops.synth_i32(n, 0xC0FFEE + 104, 0, G)
     table = {"price": price, "quantity": qty}
     cfgs = [{}]
     if G <= 2000:
         cfgs += [{"group.smem_slots": sl, "group.block": b, "group.unroll": u, "group.vec": v}
-                 for sl in (2048, 4096) for b in (256, 512) for u, v in ((2, 4), (4, 4), (2, 8))]
-        cfgs += [{"group.wp_slots": 2048}]
+                 for sl in (4096, 8192) for b in (512, 1024) for u, v in ((1, 4), (2, 4))]
     else:
-        cfgs += [{"group.block": 512}, {"group.unroll": 4}, {"group.vec": 8, "group.unroll": 2}]
+        cfgs += [{"group.pass_bits": b} for b in (0, 1, 2, 3, 4, 5)]
+        cfgs += [{"group.pass_bits": b, "group.vec": 8, "group.unroll": 1, "group.ld_hint": 2} for b in (2, 3, 4)]
+        cfgs += [{"group.pass_bits": b, "group.block": 256} for b in (2, 3)]
     for cfg in cfgs:
-        for k, v in {"group.smem_slots": -1, "group.vec": 4, "group.unroll": 2, "group.block": 256, "group.wp_slots": -1, "group.wp_unroll": 4,
-                     "group.wp_vec": 8, "group.wp_warps": 8}.items():
+        for k, v in {"group.smem_slots": -1, "group.vec": 4, "group.unroll": 2, "group.block": 512, "group.wp_slots": -1, "group.wp_unroll": 4,
+                     "group.wp_vec": 8, "group.wp_warps": 8, "group.pass_bits": -1, "group.ld_hint": 0}.items():
             wc.set_option(k, v)
         for k, v in cfg.items():
             wc.set_option(k, v)

@@ -41,11 +41,15 @@ __device__ __forceinline__ void wdb_group_row(const wdb_table &T,
 #if WDB_SMEM_SLOTS > 0
                                               const wdb_smem_table &S,
 #endif
-                                              int key, float val, i64 row) {
+                                              int key, float val, i64 row, const u32 pass_bits, const u32 pass) {
   const double dv = (double)val;
+  const u32 hsh = wdb_hash32(key);
+  // multi-pass mode (large tables): this launch only folds the keys whose hash prefix is `pass`,
+  // i.e. one contiguous, L2-sized region of the global table
+  if (pass_bits && (hsh >> (32u - pass_bits)) != pass) return;
 #if WDB_SMEM_SLOTS > 0
   if (key != WDB_KEY_EMPTY) {
-    u32 h = wdb_hash32(key) >> (32 - WDB_SMEM_LOG2);
+    u32 h = hsh >> (32 - WDB_SMEM_LOG2);
 #pragma unroll 1
     for (int p = 0; p < WDB_SMEM_PROBES; ++p) {
       const int k = S.keys[h];
@@ -65,12 +69,12 @@ __device__ __forceinline__ void wdb_group_row(const wdb_table &T,
     }
   }
 #endif
-  const i64 s = wdb_table_slot(T, key);
+  const i64 s = wdb_table_slot_h(T, key, hsh);
   if (s >= 0) { const i64 e = wdb_f64_enc(dv); wdb_table_add<WDB_NEEDS>(T, s, dv, 1ull, e, e, row); }
 }
 
 extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
-wdb_group(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T) {
+wdb_group(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T, const u32 pass_bits, const u32 pass) {
 #if WDB_SMEM_SLOTS > 0
   extern __shared__ __align__(16) unsigned char wdb_smem[];
   const wdb_smem_table S = wdb_smem_carve(wdb_smem);
@@ -82,9 +86,9 @@ wdb_group(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T) 
     if (WDB_NEEDS & WDB_NEED_FIRST_BIT) S.first[s] = 0x7fffffffffffffffll;
   }
   __syncthreads();
-#define WDB_GROUP_ROW(key, val, row) wdb_group_row(T, S, key, val, row)
+#define WDB_GROUP_ROW(key, val, row) wdb_group_row(T, S, key, val, row, pass_bits, pass)
 #else
-#define WDB_GROUP_ROW(key, val, row) wdb_group_row(T, key, val, row)
+#define WDB_GROUP_ROW(key, val, row) wdb_group_row(T, key, val, row, pass_bits, pass)
 #endif
   const i64 nvec = n / WDB_VEC;
   const i64 tile_vecs = (i64)WDB_BLOCK * WDB_UNROLL;

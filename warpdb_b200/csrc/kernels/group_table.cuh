@@ -25,6 +25,8 @@ struct wdb_table {
   long long *first;
   unsigned int *meta;
   unsigned int mask;
+  unsigned int shift;   // 32 - log2(capacity): the slot of a key is the TOP bits of its hash, so keys
+                        // whose hashes share a prefix live in one contiguous region of the table
 };
 
 // monotone map double -> signed 64-bit (a < b  <=>  enc(a) < enc(b) for non-NaN values)
@@ -45,13 +47,13 @@ __device__ __forceinline__ unsigned int wdb_hash32(int key) {
   return x;
 }
 
-// find or claim the slot of `key`; returns -1 when the table is full (overflow flag raised)
-__device__ __forceinline__ long long wdb_table_slot(const wdb_table &T, int key) {
+// find or claim the slot of `key` (hash `hsh`); returns -1 when the table is full (overflow flag raised)
+__device__ __forceinline__ long long wdb_table_slot_h(const wdb_table &T, int key, unsigned int hsh) {
   if (key == WDB_KEY_EMPTY) {
     if (T.meta[2] == 0u) atomicExch(&T.meta[2], 1u);
     return (long long)T.mask + 1;
   }
-  unsigned int h = wdb_hash32(key) & T.mask;
+  unsigned int h = hsh >> T.shift;
   const unsigned int limit = T.mask < 65535u ? T.mask + 1u : 65536u;
   for (unsigned int p = 0; p < limit; ++p) {
     int k = T.keys[h];
@@ -66,6 +68,8 @@ __device__ __forceinline__ long long wdb_table_slot(const wdb_table &T, int key)
   atomicExch(&T.meta[1], 1u);
   return -1;
 }
+
+__device__ __forceinline__ long long wdb_table_slot(const wdb_table &T, int key) { return wdb_table_slot_h(T, key, wdb_hash32(key)); }
 
 // fold one partial aggregate into slot s
 template <int NEEDS>

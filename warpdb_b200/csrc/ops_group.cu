@@ -128,7 +128,7 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   for (const auto &u : spec.used)
     if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
   p->block = (int)opt("group.block", 512);   // profiles/r01_diag_group_tuning_1e9.jsonl
-  p->unroll = (int)opt("group.unroll", 2);
+  p->unroll = (int)opt("group.unroll", 1);
   p->vec = (int)opt("group.vec", 4);
   if (p->vec != 4 && p->vec != 8) return fail("group.vec must be 4 or 8");
   // Small cardinalities (and SUM/COUNT/AVG): warp-private tables without shared-memory atomics.
@@ -143,7 +143,7 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   int64_t slots = opt("group.smem_slots", -1);
   if (slots < 0) {
     slots = 0;
-    if (expected <= 2048) { slots = 1024; while (slots < 4 * expected) slots <<= 1; }   // load factor <= 0.25: short probe chains
+    if (expected <= 2048) { slots = 1024; while (slots < 8 * expected && slots < 8192) slots <<= 1; }   // low load factor: short probe chains
   }
   if (slots & (slots - 1)) return fail("group.smem_slots must be a power of two");
   if (wp > 0) {
@@ -198,7 +198,9 @@ int wdb_agg_create(int device, int64_t expected_groups, int needs, wdb_agg_t **o
   if (get_device(device, &d)) return 1;
   if (!out) return fail("null output");
   if (needs <= 0 || needs > 15) return fail("invalid needs mask %d", needs);
+  // small tables: load factor <= 0.5; large ones (beyond the L2) trade probe length for footprint
   int64_t want = std::max<int64_t>(expected_groups, 512) * 2, cap = 1024;
+  if (expected_groups > (1 << 20)) want = expected_groups + expected_groups / 2;
   while (cap < want) cap <<= 1;
   if (cap > (1ll << 31)) return fail("aggregation table of %lld slots is too large", (long long)cap);
   wdb_agg *t = new wdb_agg();
@@ -219,6 +221,11 @@ int wdb_agg_create(int device, int64_t expected_groups, int needs, wdb_agg_t **o
   p = (char *)(((uintptr_t)p + 63) & ~(uintptr_t)63);
   t->T.meta = (unsigned *)p;
   t->T.mask = (unsigned)(cap - 1);
+  {
+    unsigned lg = 0;
+    while ((1ll << lg) < cap) ++lg;
+    t->T.shift = 32u - lg;
+  }
   if (wdb_agg_reset(t, nullptr)) { cudaFree(t->mem); delete t; return 1; }
   *out = t;
   return 0;
@@ -265,8 +272,27 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   for (const auto &u : p.spec.used) ptrs.push_back(cols[u.table_index].dptr);
   if (ptrs.empty()) ptrs.push_back(nullptr);
   long long nn = n, rb = row_base;
-  void *args[] = {ptrs.data(), &nn, &rb, &t->T};
-  return launch(k, grid, p.block, p.smem_bytes, (cudaStream_t)stream, args);
+  // Tables larger than the L2 are filled in 2^pass_bits launches; launch p folds only the keys whose
+  // hash prefix is p, which occupy one contiguous 1/2^pass_bits of the table, so the random
+  // read-modify-writes of a launch hit the L2 instead of DRAM.  Each launch re-reads the columns.
+  unsigned pass_bits = 0;
+  if (p.wp_slots == 0 && p.smem_slots == 0) {
+    const double touched = (double)t->cap * (4.0 + ((t->needs & WDB_NEED_SUM_BIT) ? 8 : 0) + ((t->needs & WDB_NEED_CNT_BIT) ? 8 : 0) +
+                                             ((t->needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) + ((t->needs & WDB_NEED_FIRST_BIT) ? 8 : 0));
+    const double budget = (double)opt("group.l2_budget_mb", 48) * 1048576.0;
+    while (pass_bits < 6 && touched / (double)(1u << pass_bits) > budget) ++pass_bits;
+    const int64_t forced = opt("group.pass_bits", -1);
+    if (forced >= 0) pass_bits = (unsigned)forced;
+  }
+  if (p.wp_slots > 0) {
+    void *args[] = {ptrs.data(), &nn, &rb, &t->T};
+    return launch(k, grid, p.block, p.smem_bytes, (cudaStream_t)stream, args);
+  }
+  for (unsigned pass = 0; pass < (1u << pass_bits); ++pass) {
+    void *args[] = {ptrs.data(), &nn, &rb, &t->T, &pass_bits, &pass};
+    if (launch(k, grid, p.block, p.smem_bytes, (cudaStream_t)stream, args)) return 1;
+  }
+  return 0;
 }
 
 int wdb_agg_merge(wdb_agg_t *t, void *stream, const int32_t *d_keys, const double *d_sums, const int64_t *d_counts,

@@ -35,8 +35,8 @@ static int run_shard(ShardJob *job, const wdb_col_t *h_cols, int ncols, const ch
   std::vector<UsedCol> used = find_used_columns(h_cols, ncols, {expr, has_cond ? cond : ""});
   for (const auto &u : used)
     if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
-  const int64_t chunk = std::min<int64_t>(rows, std::max<int64_t>(1 << 16, opt("multi.chunk_rows", 1 << 24)));
-  const int nslots = (int)std::max<int64_t>(1, std::min<int64_t>(opt("multi.slots", 3), (rows + chunk - 1) / chunk));
+  const int64_t chunk = std::min<int64_t>(rows, std::max<int64_t>(1 << 16, opt("multi.chunk_rows", 1 << 27)));
+  const int nslots = (int)std::max<int64_t>(1, std::min<int64_t>(opt("multi.slots", 2), (rows + chunk - 1) / chunk));
   size_t row_bytes = 4;
   for (const auto &u : used) row_bytes += dtype_size(u.dtype);
   char *pool = nullptr;
