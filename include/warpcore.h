@@ -135,6 +135,25 @@ int wdb_sort_pairs(int device, void *stream, int32_t *d_keys, float *d_vals, int
  * zone maps (per-tile min/max) used for pruning; new work, the reference's analyze_condition is
  * a stub (src/optimizer.cpp:13-17). */
 int wdb_column_minmax(int device, void *stream, const wdb_col_t *col, double *h_min, double *h_max);
+/* Zone map: min/max of every zone of zone_rows rows (power of two >= 2048; 0 = 4096), built in one
+ * streaming pass (typically at load time).  Values are recorded as the filter kernel sees them when
+ * the column is compared with a float literal (integers converted to float). */
+typedef struct wdb_zonemap wdb_zonemap_t;
+int wdb_zonemap_build(int device, void *stream, const wdb_col_t *col, int64_t zone_rows, wdb_zonemap_t **out);
+int wdb_zonemap_destroy(wdb_zonemap_t *z);
+int wdb_zonemap_info(const wdb_zonemap_t *z, int64_t *zone_rows, int64_t *nzones);
+/* one `column <op> constant` term of a conjunction; op: 0 '>' 1 '>=' 2 '<' 3 '<=' 4 '==' 5 '!=' */
+typedef struct wdb_prune {
+  const wdb_zonemap_t *zonemap;
+  int op;
+  double value;
+} wdb_prune_t;
+/* wdb_project_filter with zone-map pruning: `cond` is still evaluated on every row that is read,
+ * preds (implied by cond: the AND-ed col-vs-constant terms of it) only decide which zones are read
+ * at all.  Results are identical to wdb_project_filter.  h_zones_live (optional) = zones not pruned. */
+int wdb_project_filter_pruned(int device, void *stream, const wdb_col_t *cols, int ncols, const char *expr,
+                              const char *cond, float *d_out, int64_t n, int mode, int64_t *d_count,
+                              int64_t *h_count, const wdb_prune_t *preds, int npreds, int64_t *h_zones_live);
 
 /* ---- multi-GPU: run_multi_gpu_jit_host (include/multi_gpu_utils.hpp:10-12,
  * src/multi_gpu_utils.cpp:5-63).  Host columns in, host floats out; rows are split into

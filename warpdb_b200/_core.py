@@ -23,6 +23,7 @@ SYMBOLS = [
     "wdb_set_option", "wdb_get_option", "wdb_get_stats", "wdb_project_filter", "wdb_agg_create", "wdb_agg_destroy",
     "wdb_agg_reset", "wdb_agg_consume", "wdb_agg_merge", "wdb_agg_size", "wdb_agg_export", "wdb_group_agg",
     "wdb_topk", "wdb_sort_float", "wdb_sort_pairs", "wdb_column_minmax", "wdb_multi_project_filter_host",
+    "wdb_zonemap_build", "wdb_zonemap_destroy", "wdb_zonemap_info", "wdb_project_filter_pruned",
     "wdb_shard_range", "wdb_synth_f32", "wdb_synth_i32", "wdb_debug_compile", "wdb_free",
 ]
 
@@ -33,6 +34,13 @@ class WarpcoreError(RuntimeError):
 
 class Col(C.Structure):
     _fields_ = [("name", C.c_char_p), ("dtype", C.c_int), ("dptr", C.c_void_p), ("len", C.c_int64)]
+
+
+class Prune(C.Structure):
+    _fields_ = [("zonemap", C.c_void_p), ("op", C.c_int), ("value", C.c_double)]
+
+
+PRUNE_OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "==": 4, "!=": 5}
 
 
 class Stats(C.Structure):
@@ -75,6 +83,10 @@ def lib():
     L.wdb_sort_pairs.argtypes = [ci, vp, vp, vp, i64, ci]
     L.wdb_column_minmax.argtypes = [ci, vp, PC, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.wdb_multi_project_filter_host.argtypes = [ci, C.POINTER(ci), PC, ci, cp, cp, vp, i64, ci, P64]
+    L.wdb_zonemap_build.argtypes = [ci, vp, PC, i64, C.POINTER(vp)]
+    L.wdb_zonemap_destroy.argtypes = [vp]
+    L.wdb_zonemap_info.argtypes = [vp, P64, P64]
+    L.wdb_project_filter_pruned.argtypes = [ci, vp, PC, ci, cp, cp, vp, i64, ci, vp, P64, C.POINTER(Prune), ci, P64]
     L.wdb_shard_range.argtypes = [i64, ci, ci, P64, P64]
     L.wdb_synth_f32.argtypes = [ci, vp, vp, i64, C.c_uint64, C.c_float, C.c_float, i64]
     L.wdb_synth_i32.argtypes = [ci, vp, vp, i64, C.c_uint64, C.c_int32, C.c_int32, i64]

@@ -84,7 +84,10 @@ PYBIND11_MODULE(pywarpdb, m) {
            },
            py::arg("expr"), py::arg("shared_memory") = false,
            "Return result as Arrow C Data Interface capsules (ArrowArray, ArrowSchema).")
-      .def("num_rows", &WarpDB::num_rows);
+      .def("num_rows", &WarpDB::num_rows)
+      .def("set_zone_pruning", &WarpDB::set_zone_pruning)
+      .def("last_zones_live", &WarpDB::last_zones_live)
+      .def("last_zones_total", &WarpDB::last_zones_total);
 
   // front-end helpers (parity tests against tests/golden/frontend.json)
   m.def("expr_to_cuda", [](const std::string &text) { return parse_expression(tokenize(text))->to_cuda_expr(); });

@@ -56,7 +56,7 @@ void split_where(const std::string &text, std::string *expr_part, std::string *w
   }
 }
 
-struct ParsedExpr { std::string expr_cuda, cond_cuda; };
+struct ParsedExpr { std::string expr_cuda, cond_cuda; ASTNodePtr cond_ast; };
 
 ParsedExpr parse_expr_where(const std::string &text, const std::unordered_set<std::string> &cols, bool wrap_errors) {
   std::string expr_part, where_part;
@@ -80,6 +80,7 @@ ParsedExpr parse_expr_where(const std::string &text, const std::unordered_set<st
         ASTNodePtr c = parse_expression(tokenize(where_part));
         validate_ast(c.get(), cols);
         out.cond_cuda = c->to_cuda_expr();
+        out.cond_ast = std::move(c);
       } catch (const std::exception &e) {
         throw std::runtime_error(std::string("Failed to parse WHERE clause: ") + e.what());
       }
@@ -87,6 +88,7 @@ ParsedExpr parse_expr_where(const std::string &text, const std::unordered_set<st
       ASTNodePtr c = parse_expression(tokenize(where_part));
       validate_ast(c.get(), cols);
       out.cond_cuda = c->to_cuda_expr();
+      out.cond_ast = std::move(c);
     }
   }
   return out;
@@ -214,7 +216,77 @@ WarpDB::WarpDB(Table device_table, HostTable host_table)
     : table_(std::move(device_table)), host_table_(std::move(host_table)), owns_device_(false) {}
 
 WarpDB::~WarpDB() {
+  for (auto &kv : zonemaps_)
+    if (kv.second) wdb_zonemap_destroy(static_cast<wdb_zonemap_t *>(kv.second));
   if (owns_device_) free_table(table_);
+}
+
+// AND-ed `column <op> constant` terms of a condition (either operand order); anything else in the
+// conjunction is simply not used for pruning -- a subset of a conjunction is still implied by it.
+std::vector<WarpDB::PruneTerm> WarpDB::prune_terms(const ASTNode *cond) const {
+  std::vector<PruneTerm> out;
+  std::vector<const ASTNode *> stack{cond};
+  static const char *const ops[] = {">", ">=", "<", "<=", "==", "!="};
+  static const int mirrored[] = {2, 3, 0, 1, 4, 5};
+  while (!stack.empty()) {
+    const ASTNode *n = stack.back();
+    stack.pop_back();
+    const auto *b = dynamic_cast<const BinaryOpNode *>(n);
+    if (!b) continue;
+    if (b->op == "&&") { stack.push_back(b->left.get()); stack.push_back(b->right.get()); continue; }
+    int op = -1;
+    for (int i = 0; i < 6; ++i)
+      if (b->op == ops[i]) op = i;
+    if (op < 0) continue;
+    const auto *lv = dynamic_cast<const VariableNode *>(b->left.get());
+    const auto *rv = dynamic_cast<const VariableNode *>(b->right.get());
+    const auto *lc = dynamic_cast<const ConstantNode *>(b->left.get());
+    const auto *rc = dynamic_cast<const ConstantNode *>(b->right.get());
+    if (lv && rc) out.push_back({lv->name, op, static_cast<double>(std::stof(rc->value))});
+    else if (lc && rv) out.push_back({rv->name, mirrored[op], static_cast<double>(std::stof(lc->value))});
+  }
+  return out;
+}
+
+void *WarpDB::zonemap_for(const std::string &column) {
+  auto it = zonemaps_.find(column);
+  if (it != zonemaps_.end()) return it->second;
+  void *zm = nullptr;
+  for (const auto &c : table_.columns)
+    if (c.name == column && c.type != DataType::String && c.device_ptr && table_.num_rows > 0) {
+      const wdb_col_t col{c.name.c_str(), static_cast<int>(c.type), c.device_ptr, table_.num_rows};
+      wdb_zonemap_t *z = nullptr;
+      if (wdb_zonemap_build(0, nullptr, &col, 0, &z)) raise_core();
+      zm = z;
+    }
+  zonemaps_[column] = zm;
+  return zm;
+}
+
+// fused filter+project of the whole table, zone-pruned when the condition allows it
+int WarpDB::filter_project(const std::string &expr, const std::string &cond, const ASTNode *cond_ast, float *d_out, int mode,
+                           long long *count) {
+  const std::vector<wdb_col_t> dcols = describe(table_);
+  int64_t cnt = 0;
+  last_zones_live_ = last_zones_total_ = -1;
+  std::vector<wdb_prune_t> preds;
+  if (zone_pruning_ && cond_ast && table_.num_rows >= 8192)
+    for (const auto &t : prune_terms(cond_ast))
+      if (void *zm = zonemap_for(t.column)) preds.push_back(wdb_prune_t{static_cast<const wdb_zonemap_t *>(zm), t.op, t.value});
+  int rc;
+  if (!preds.empty()) {
+    int64_t live = 0, zr = 0, nz = 0;
+    rc = wdb_project_filter_pruned(0, nullptr, dcols.data(), static_cast<int>(dcols.size()), expr.c_str(), cond.c_str(), d_out,
+                                   table_.num_rows, mode, nullptr, &cnt, preds.data(), static_cast<int>(preds.size()), &live);
+    wdb_zonemap_info(preds[0].zonemap, &zr, &nz);
+    last_zones_live_ = live;
+    last_zones_total_ = nz;
+  } else {
+    rc = wdb_project_filter(0, nullptr, dcols.data(), static_cast<int>(dcols.size()), expr.c_str(), cond.c_str(), d_out,
+                            table_.num_rows, mode, nullptr, &cnt);
+  }
+  if (count) *count = cnt;
+  return rc;
 }
 
 std::vector<float> WarpDB::query(const std::string &expr) {
@@ -225,13 +297,9 @@ std::vector<float> WarpDB::query(const std::string &expr) {
   refresh_udf_source();
   const size_t n = static_cast<size_t>(table_.num_rows);
   DeviceBuffer out(sizeof(float) * n);
-  const std::vector<wdb_col_t> dcols = describe(table_);
-  int64_t count = 0;
   // the reference leaves rows failing WHERE uninitialised in a fresh cudaMalloc buffer
   // (src/jit.cpp:55-61, src/warpdb.cpp:243-256); they are defined as 0.0f here
-  if (wdb_project_filter(0, nullptr, dcols.data(), static_cast<int>(dcols.size()), p.expr_cuda.c_str(), p.cond_cuda.c_str(),
-                         out.as<float>(), table_.num_rows, WDB_DENSE_ZERO, nullptr, &count))
-    raise_core();
+  if (filter_project(p.expr_cuda, p.cond_cuda, p.cond_ast.get(), out.as<float>(), WDB_DENSE_ZERO, nullptr)) raise_core();
   return download<float>(out.p, n);
 }
 
@@ -339,8 +407,8 @@ std::vector<float> WarpDB::query_sql(const std::string &sql) {
   }
   // plain SELECT: surviving rows in row order (stable compaction), then OFFSET / LIMIT
   DeviceBuffer out(sizeof(float) * static_cast<size_t>(n));
-  int64_t count = 0;
-  if (wdb_project_filter(0, nullptr, dcols.data(), nc, sel.c_str(), cond.c_str(), out.as<float>(), n, WDB_COMPACT, nullptr, &count)) raise_core();
+  long long count = 0;
+  if (filter_project(sel, cond, ast.where ? ast.where->get() : nullptr, out.as<float>(), WDB_COMPACT, &count)) raise_core();
   const int64_t off = std::min<int64_t>(ast.offset ? std::max(ast.offset->count, 0) : 0, count);
   int64_t m = count - off;
   if (ast.limit) m = std::min<int64_t>(m, std::max(ast.limit->count, 0));

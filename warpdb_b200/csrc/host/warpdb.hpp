@@ -1,6 +1,7 @@
 // warpdb.hpp -- the WarpDB facade with the reference's public signatures (include/warpdb.hpp:11-48),
 // running on the B200-native core (include/warpcore.h).
 #pragma once
+#include <map>
 #include <string>
 #include <vector>
 
@@ -33,8 +34,23 @@ public:
   int num_rows() const { return table_.num_rows; }
   const Table &table() const { return table_; }
 
+  // zone maps (per-4096-row min/max) are built lazily per column and drive pruning of
+  // `col <op> const` terms of WHERE clauses; disable to run every query unpruned
+  void set_zone_pruning(bool on) { zone_pruning_ = on; }
+  long long last_zones_live() const { return last_zones_live_; }
+  long long last_zones_total() const { return last_zones_total_; }
+
 private:
+  struct PruneTerm { std::string column; int op; double value; };
+  std::vector<PruneTerm> prune_terms(const ASTNode *cond) const;
+  void *zonemap_for(const std::string &column);   // wdb_zonemap_t*, nullptr if not prunable
+  int filter_project(const std::string &expr, const std::string &cond, const ASTNode *cond_ast, float *d_out, int mode,
+                     long long *count);
+
   Table table_;
   HostTable host_table_;
   bool owns_device_ = true;
+  bool zone_pruning_ = true;
+  std::map<std::string, void *> zonemaps_;
+  long long last_zones_live_ = -1, last_zones_total_ = -1;
 };

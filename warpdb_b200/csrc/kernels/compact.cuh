@@ -401,13 +401,25 @@ wdb_compact_bulk(const wdb_cols C, float *__restrict__ out, float *__restrict__ 
 // No tickets, no look-back, no block barriers: both kernels are plain streaming kernels.  The price
 // is reading the columns the condition needs a second time: (cond bytes) + (all used bytes) +
 // 4*NOUT*selectivity per row instead of (all used bytes) + 4*NOUT*selectivity.
+#if WDB_PRUNE
+// zone-map pruning: a chunk whose zone cannot contain a passing row is neither loaded nor counted
+#define WDB_ZONE_ARGS , const unsigned char *__restrict__ zmask, const int zshift
+#define WDB_CHUNK_DEAD(chunk) (zmask[((chunk) * WDB_WARP_ROWS) >> zshift] == 0)
+#else
+#define WDB_ZONE_ARGS
+#define WDB_CHUNK_DEAD(chunk) false
+#endif
 extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
-wdb_count(const wdb_cols C, const i64 n, u32 *__restrict__ counts, const i64 nchunks, const float wdb_tau) {
+wdb_count(const wdb_cols C, const i64 n, u32 *__restrict__ counts, const i64 nchunks, const float wdb_tau WDB_ZONE_ARGS) {
   const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const i64 chunk = (i64)blockIdx.x * WDB_NWARPS + warp;
   if (chunk >= nchunks) return;
   const i64 row0 = chunk * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
   u32 cnt = 0;
+  if (WDB_CHUNK_DEAD(chunk)) {
+    if (lane == 0) counts[chunk] = 0u;
+    return;
+  }
   if ((chunk + 1) * WDB_WARP_ROWS <= n) {
     wdb_rows R[WDB_UNROLL];
 #pragma unroll
@@ -435,7 +447,7 @@ wdb_count(const wdb_cols C, const i64 n, u32 *__restrict__ counts, const i64 nch
 
 extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
 wdb_scatter(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n,
-            const i64 *__restrict__ offsets, const i64 nchunks, const float wdb_tau, const i64 out_cap) {
+            const i64 *__restrict__ offsets, const i64 nchunks, const float wdb_tau, const i64 out_cap WDB_ZONE_ARGS) {
   __shared__ float s_stage[WDB_NWARPS][WDB_WARP_ROWS];
 #if WDB_NOUT == 2
   __shared__ float s_stage2[WDB_NWARPS][WDB_WARP_ROWS];
@@ -444,6 +456,7 @@ wdb_scatter(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
   const u32 lt = wdb_lanemask_lt();
   const i64 chunk = (i64)blockIdx.x * WDB_NWARPS + warp;
   if (chunk >= nchunks) return;
+  if (WDB_CHUNK_DEAD(chunk)) return;
   const i64 row0 = chunk * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
   const i64 g0 = offsets[chunk];
   u32 flags[WDB_UNROLL];

@@ -53,8 +53,27 @@ __device__ __forceinline__ void wdb_emit_row(const wdb_cols &C, float *__restric
 // tile, lanes interleaved so every warp instruction touches one contiguous 512 B / 1 KB span; all
 // loads of a tile are issued before the first use (memory-level parallelism).  Launched either
 // with one CTA per tile (variant 0) or as a persistent grid-stride loop (variant 1).
+#if WDB_PRUNE
+// Zone-map pruning: zmask[row >> zshift] == 0 means "no row of this zone can pass the condition"
+// (decided on the host side of the ABI from per-zone min/max); such vectors are never loaded.
+#define WDB_ZONE_ARGS , const unsigned char *__restrict__ zmask, const int zshift
+#define WDB_ZONE_LIVE(row) (zmask[(row) >> zshift] != 0)
+#else
+#define WDB_ZONE_ARGS
+#define WDB_ZONE_LIVE(row) true
+#endif
+
+__device__ __forceinline__ void wdb_emit_pruned(float *__restrict__ out, i64 row) {
+#if WDB_MODE == 2
+  float z[WDB_VEC];
+#pragma unroll
+  for (int j = 0; j < WDB_VEC; ++j) z[j] = 0.0f;
+  wdb_store_vec(out, row, z);
+#endif
+}
+
 extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
-wdb_project(const wdb_cols C, float *__restrict__ out, const i64 n) {
+wdb_project(const wdb_cols C, float *__restrict__ out, const i64 n WDB_ZONE_ARGS) {
   const i64 nvec = n / WDB_VEC;
   const i64 tile_vecs = (i64)WDB_BLOCK * WDB_UNROLL;
   const i64 ntiles = (nvec + tile_vecs - 1) / tile_vecs;
@@ -62,15 +81,25 @@ wdb_project(const wdb_cols C, float *__restrict__ out, const i64 n) {
     const i64 v0 = tile * tile_vecs + threadIdx.x;
     wdb_rows R[WDB_UNROLL];
     if ((tile + 1) * tile_vecs <= nvec) {
+      bool live[WDB_UNROLL];
 #pragma unroll
-      for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows(C, (v0 + (i64)u * WDB_BLOCK) * WDB_VEC, R[u]);
+      for (int u = 0; u < WDB_UNROLL; ++u) live[u] = WDB_ZONE_LIVE((v0 + (i64)u * WDB_BLOCK) * WDB_VEC);
 #pragma unroll
-      for (int u = 0; u < WDB_UNROLL; ++u) wdb_emit_vec(out, (v0 + (i64)u * WDB_BLOCK) * WDB_VEC, R[u]);
+      for (int u = 0; u < WDB_UNROLL; ++u)
+        if (live[u]) wdb_load_rows(C, (v0 + (i64)u * WDB_BLOCK) * WDB_VEC, R[u]);
+#pragma unroll
+      for (int u = 0; u < WDB_UNROLL; ++u) {
+        if (live[u]) wdb_emit_vec(out, (v0 + (i64)u * WDB_BLOCK) * WDB_VEC, R[u]);
+        else wdb_emit_pruned(out, (v0 + (i64)u * WDB_BLOCK) * WDB_VEC);
+      }
     } else {
 #pragma unroll
       for (int u = 0; u < WDB_UNROLL; ++u) {
         const i64 v = v0 + (i64)u * WDB_BLOCK;
-        if (v < nvec) { wdb_load_rows(C, v * WDB_VEC, R[u]); wdb_emit_vec(out, v * WDB_VEC, R[u]); }
+        if (v < nvec) {
+          if (WDB_ZONE_LIVE(v * WDB_VEC)) { wdb_load_rows(C, v * WDB_VEC, R[u]); wdb_emit_vec(out, v * WDB_VEC, R[u]); }
+          else wdb_emit_pruned(out, v * WDB_VEC);
+        }
       }
     }
   }

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kScanBlock) scan_add_kernel(long long *__restr
 struct CompactPlan { GenSpec spec; int block, unroll, vec, variant; int64_t tile_rows; bool two; size_t smem; };
 
 static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, const char *expr2, const char *cond,
-                        bool check_alignment, int thresh, CompactPlan *p) {
+                        bool check_alignment, int thresh, CompactPlan *p, bool prune = false) {
   GenSpec &spec = p->spec;
   spec.kind = "compact";
   if (!cond || !*cond) cond = "true";
@@ -80,6 +80,7 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
   if (unroll < 1 || unroll > 8) return fail("compact.unroll must be in [1,8]");
   const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)vec * 4);
   if (!aligned && variant == 1) variant = 2;       // bulk copies need 16-byte aligned columns
+  if (prune) variant = 2;                          // zone-map pruning is wired into the two-pass kernels
   size_t row_bytes = 0;
   for (const auto &u : spec.used) row_bytes += dtype_size(u.dtype);
   if (variant != 1)
@@ -93,7 +94,7 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
   spec.defines = {{"WDB_VEC", vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("compact.ld_hint", 0)},
                   {"WDB_ST_HINT", 0}, {"WDB_BLOCK", block}, {"WDB_UNROLL", unroll}, {"WDB_NOUT", two ? 2 : 1},
                   {"WDB_THRESH", two ? thresh : 0}, {"WDB_MIN_CTAS", opt("compact.min_ctas", 1)},
-                  {"WDB_LB", opt("compact.lookback", variant == 1 ? 4 : 1)}, {"WDB_BULK", variant == 1 ? 1 : 0}, {"WDB_TWOPASS", variant == 2 ? 1 : 0}};
+                  {"WDB_LB", opt("compact.lookback", variant == 1 ? 4 : 1)}, {"WDB_BULK", variant == 1 ? 1 : 0}, {"WDB_TWOPASS", variant == 2 ? 1 : 0}, {"WDB_PRUNE", prune ? 1 : 0}};
   if (variant == 1) spec.defines.push_back({"WDB_TILE", p->tile_rows});
   spec.fns.push_back({"expr", "float", expr});
   if (two) spec.fns.push_back({"expr2", "float", expr2});
@@ -112,9 +113,10 @@ int gen_compact_source(const wdb_col_t *cols, int ncols, const char *expr, const
 
 int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr, const char *expr2,
                    const char *cond, float *d_out, float *d_out2, int64_t n, int64_t *d_count, int64_t *h_count,
-                   int thresh, float tau, int64_t out_cap) {
+                   int thresh, float tau, int64_t out_cap, const unsigned char *zmask, int zshift) {
   CompactPlan p;
-  if (plan_compact(cols, ncols, expr, expr2, cond, true, thresh, &p)) return 1;
+  if (plan_compact(cols, ncols, expr, expr2, cond, true, thresh, &p, zmask != nullptr)) return 1;
+  if (zmask && (1ll << zshift) < p.tile_rows / (p.block / 32)) return fail("zone size %lld is smaller than a compaction chunk", 1ll << zshift);
   GenSpec &spec = p.spec;
   const int block = p.block;
   const int64_t tile_rows = p.tile_rows;
@@ -143,7 +145,7 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
       long long nn = n, nc = nchunks, cap = out_cap;
       const unsigned grid = (unsigned)((nchunks + nwarps - 1) / nwarps);
       {
-        void *args[] = {ptrs.data(), &nn, &d_counts, &nc, &tau};
+        void *args[] = {ptrs.data(), &nn, &d_counts, &nc, &tau, &zmask, &zshift};
         if (launch(kc, grid, block, 0, stream, args)) return 1;
       }
       scan_local_kernel<<<(unsigned)nsb, kScanBlock, 0, stream>>>(d_counts, d_offs, d_sums, nchunks);
@@ -152,7 +154,7 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
       stats().launches += 3;
       WDB_CUDA(cudaGetLastError());
       {
-        void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_offs, &nc, &tau, &cap};
+        void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_offs, &nc, &tau, &cap, &zmask, &zshift};
         if (launch(ks, grid, block, 0, stream, args)) return 1;
       }
     }
@@ -207,7 +209,7 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
 
 int run_compact(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr, const char *expr2,
                 const char *cond, float *d_out, float *d_out2, int64_t n, int64_t *d_count, int64_t *h_count) {
-  return run_compact_ex(d, stream, cols, ncols, expr, expr2, cond, d_out, d_out2, n, d_count, h_count, 0, 0.0f, n);
+  return run_compact_ex(d, stream, cols, ncols, expr, expr2, cond, d_out, d_out2, n, d_count, h_count, 0, 0.0f, n, nullptr, 0);
 }
 
 }  // namespace wdb

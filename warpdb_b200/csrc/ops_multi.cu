@@ -14,7 +14,7 @@
 
 namespace wdb {
 int run_project(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr, const char *cond,
-                float *d_out, int64_t n, int mode);
+                float *d_out, int64_t n, int mode, const unsigned char *zmask = nullptr, int zshift = 0);
 int run_compact(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr, const char *expr2,
                 const char *cond, float *d_out, float *d_out2, int64_t n, int64_t *d_count, int64_t *h_count);
 

@@ -16,7 +16,7 @@
 namespace wdb {
 int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr, const char *expr2,
                    const char *cond, float *d_out, float *d_out2, int64_t n, int64_t *d_count, int64_t *h_count,
-                   int thresh, float tau, int64_t out_cap);
+                   int thresh, float tau, int64_t out_cap, const unsigned char *zmask = nullptr, int zshift = 0);
 int sort_f32(Device *d, cudaStream_t s, float *d_keys, float *d_payload, long long n, bool ascending);
 
 struct TopkPlan { GenSpec spec; int block, unroll, vec, K; };

@@ -402,6 +402,8 @@ __global__ void __launch_bounds__(256) wdb_synth_i32_kernel(int *__restrict__ ou
 namespace wdb {
 int run_compact(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr, const char *key_expr,
                 const char *cond, float *d_out, float *d_out2, int64_t n, int64_t *d_count, int64_t *h_count);
+int run_project(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr, const char *cond,
+                float *d_out, int64_t n, int mode, const unsigned char *zmask = nullptr, int zshift = 0);
 
 struct ProjectPlan {
   GenSpec spec;
@@ -411,7 +413,7 @@ struct ProjectPlan {
 };
 
 static int plan_project(const wdb_col_t *cols, int ncols, const char *expr, const char *cond, const float *d_out,
-                        int mode, ProjectPlan *p, bool check_alignment) {
+                        int mode, ProjectPlan *p, bool check_alignment, bool prune = false) {
   const bool has_cond = cond && *cond;
   p->spec.kind = "project";
   p->spec.used = find_used_columns(cols, ncols, {expr, has_cond ? cond : ""});
@@ -428,6 +430,7 @@ static int plan_project(const wdb_col_t *cols, int ncols, const char *expr, cons
   if (p->unroll < 1 || p->unroll > 16) return fail("project.unroll must be in [1,16]");
   // dense-untouched output cannot leave through a bulk store
   if (p->variant == 2 && has_cond && mode != WDB_DENSE_ZERO) p->variant = 0;
+  if (prune) p->variant = 0;
   if (p->variant == 2) {
     if (p->stages < 2 || p->stages > 8) return fail("project.stages must be in [2,8]");
     if (p->tile % (4 * p->block)) return fail("project.tile must be a multiple of 4*project.block");
@@ -444,6 +447,7 @@ static int plan_project(const wdb_col_t *cols, int ncols, const char *expr, cons
   D.push_back({"WDB_MODE", mode == WDB_DENSE_ZERO ? 2 : 0});
   D.push_back({"WDB_HAS_COND", has_cond ? 1 : 0});
   D.push_back({"WDB_BULK", p->variant == 2 ? 1 : 0});
+  D.push_back({"WDB_PRUNE", prune ? 1 : 0});
   if (p->variant == 2) {
     D.push_back({"WDB_TILE", p->tile});
     D.push_back({"WDB_STAGES", p->stages});
@@ -456,9 +460,9 @@ static int plan_project(const wdb_col_t *cols, int ncols, const char *expr, cons
 }
 
 int run_project(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols, const char *expr,
-                       const char *cond, float *d_out, int64_t n, int mode) {
+                       const char *cond, float *d_out, int64_t n, int mode, const unsigned char *zmask, int zshift) {
   ProjectPlan p;
-  if (plan_project(cols, ncols, expr, cond, d_out, mode, &p, true)) return 1;
+  if (plan_project(cols, ncols, expr, cond, d_out, mode, &p, true, zmask != nullptr)) return 1;
   Kernel k;
   if (get_kernel(d, gen_source(p.spec), "wdb_project.cu", p.entry, &k)) return 1;
   if (n == 0) return 0;
@@ -466,7 +470,7 @@ int run_project(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols
   for (const auto &u : p.spec.used) ptrs.push_back(cols[u.table_index].dptr);
   if (ptrs.empty()) ptrs.push_back(nullptr);
   long long nn = n;
-  void *args[] = {ptrs.data(), &d_out, &nn};
+  void *args[] = {ptrs.data(), &d_out, &nn, &zmask, &zshift};   // the last two only exist in pruned instantiations
   if (p.variant == 2) {
     size_t row_bytes = 4;
     for (const auto &u : p.spec.used) row_bytes += dtype_size(u.dtype);

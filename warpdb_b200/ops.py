@@ -193,3 +193,47 @@ def sort_pairs(keys, vals, ascending=True):
     dev = keys.device.index or 0
     wc.check(wc.lib().wdb_sort_pairs(dev, _stream(dev), keys.data_ptr(), vals.data_ptr(), keys.numel(), int(ascending)))
     return keys, vals
+
+
+class ZoneMap:
+    """Per-zone min/max of one column (wdb_zonemap_*), built in one streaming pass."""
+
+    def __init__(self, column, name="col", zone_rows=0):
+        self.device = column.device.index or 0
+        self.rows = column.shape[0]
+        self.handle = C.c_void_p()
+        cols, _ = wc.make_cols(schema_of({name: column}))
+        wc.check(wc.lib().wdb_zonemap_build(self.device, _stream(self.device), cols, zone_rows, C.byref(self.handle)))
+        zr, nz = C.c_int64(0), C.c_int64(0)
+        wc.check(wc.lib().wdb_zonemap_info(self.handle, C.byref(zr), C.byref(nz)))
+        self.zone_rows, self.nzones = zr.value, nz.value
+
+    def close(self):
+        if self.handle:
+            wc.lib().wdb_zonemap_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def project_filter_pruned(table, expr, cond, preds, mode=wc.DENSE_ZERO, out=None, sync=True):
+    """wdb_project_filter_pruned.  preds: list of (ZoneMap, op, constant) with op in > >= < <= == != and
+    every term implied by `cond`.  Returns (out, count, zones_live)."""
+    dev = _dev_index(table)
+    n = num_rows(table)
+    if out is None:
+        out = torch.empty(max(n, 1), dtype=torch.float32, device=f"cuda:{dev}")[:n]
+    cols, nc = wc.make_cols(schema_of(table))
+    arr = (wc.Prune * max(len(preds), 1))()
+    for i, (zm, op, value) in enumerate(preds):
+        arr[i].zonemap = zm.handle
+        arr[i].op = wc.PRUNE_OPS[op]
+        arr[i].value = float(value)
+    cnt, live = C.c_int64(0), C.c_int64(0)
+    wc.check(wc.lib().wdb_project_filter_pruned(dev, _stream(dev), cols, nc, wc.enc(expr), wc.enc(cond), out.data_ptr(), n, mode, None,
+                                                C.byref(cnt) if sync else None, arr, len(preds), C.byref(live) if sync else None))
+    return out, (cnt.value if sync else None), (live.value if sync else None)

@@ -57,6 +57,12 @@ class CudaBackend:
             tab.reset()
         return tab
 
+    def group_local(self, table, val, key, cond, needs, expected, agg, order):
+        """Single-GPU GROUP BY: aggregate and export once."""
+        tab = self._table("partial", expected, needs)
+        tab.consume(table, val, key, cond, row_base=0)
+        return tab.export(agg, order, raw=True)
+
     def group_partials(self, table, val, key, cond, needs, expected, row_base):
         tab = self._table("partial", expected, needs)
         tab.consume(table, val, key, cond, row_base=row_base)
@@ -160,6 +166,8 @@ class ShardedDB:
         """GROUP BY over all shards.  Every rank returns the same dict(keys, vals, ...) of final groups."""
         from .ops import needs_for
         needs = needs_for(agg, order)
+        if self.world == 1 and hasattr(self.backend, "group_local"):
+            return self.backend.group_local(self.table, val, key, cond, needs, expected_groups, agg, order)
         part = self.backend.group_partials(self.table, val, key, cond, needs, expected_groups, self.row0)
         if self.world == 1:
             return self.backend.merge_partials([part], needs, expected_groups, agg, order)
