@@ -45,11 +45,8 @@ struct Device {
   std::string arch;          // "sm_100a"
   std::mutex mu;
   std::unordered_map<std::string, Kernel> cache;
-  void *scratch = nullptr;   // grow-only scratch (tile status words, counters, partial results)
-  size_t scratch_bytes = 0;
 };
 int get_device(int id, Device **out);                 // initialises on first use; makes it current
-int ensure_scratch(Device *d, size_t bytes);          // d->scratch valid for `bytes` afterwards
 
 // ---- code generation ---------------------------------------------------------------------------
 struct UsedCol { int table_index; std::string name; int dtype; };

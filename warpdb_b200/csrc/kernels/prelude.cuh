@@ -109,6 +109,24 @@ template <class T> __device__ __forceinline__ void wdb_load_vec(const T *__restr
   for (int j = 0; j < WDB_VEC; ++j) o[j] = __ldg(p + row + j);
 #endif
 }
+// coherent (read-write data) vector load of WDB_VEC floats: used to blend into the output buffer
+__device__ __forceinline__ void wdb_load_out_vec(const float *p, i64 row, float (&o)[WDB_VEC]) {
+#if WDB_ALIGNED && WDB_VEC == 8
+  u32 r[8];
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p + row) : "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(r[j]);
+#elif WDB_ALIGNED
+  u32 r[4];
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p + row) : "memory");
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = __uint_as_float(r[j]);
+#else
+#pragma unroll
+  for (int j = 0; j < WDB_VEC; ++j) o[j] = p[row + j];
+#endif
+}
 __device__ __forceinline__ void wdb_store_vec(float *__restrict__ p, i64 row, const float (&v)[WDB_VEC]) {
 #if WDB_ALIGNED
 #if WDB_VEC == 8

@@ -24,9 +24,19 @@ __device__ __forceinline__ void wdb_emit_vec(float *__restrict__ out, i64 row, c
     for (int j = 0; j < WDB_VEC; ++j) v[j] = WDB_EXPR(R, j);
     wdb_store_vec(out, row, v);
   } else if (m) {
+#if WDB_ALIGNED
+    // partially passing vector: read-modify-write of the whole vector (one 256-bit load + store)
+    // instead of up to WDB_VEC predicated 4-byte stores, which cost 2.6 ms per 1e9 rows at 50 %
+    wdb_load_out_vec(out, row, v);
+#pragma unroll
+    for (int j = 0; j < WDB_VEC; ++j)
+      if ((m >> j) & 1u) v[j] = WDB_EXPR(R, j);
+    wdb_store_vec(out, row, v);
+#else
 #pragma unroll
     for (int j = 0; j < WDB_VEC; ++j)
       if ((m >> j) & 1u) out[row + j] = WDB_EXPR(R, j);
+#endif
   }
 #endif
 #else

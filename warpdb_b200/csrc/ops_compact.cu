@@ -131,8 +131,9 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
     // scratch: [0,8) total, [64, ...) offsets i64[nchunks], block sums i64[nsb], counts u32[nchunks]
     const size_t off_bytes = 8 * (size_t)std::max<int64_t>(nchunks, 1), sum_bytes = 8 * (size_t)std::max<int64_t>(nsb, 1);
     const size_t need = 64 + off_bytes + sum_bytes + 4 * (size_t)std::max<int64_t>(nchunks, 1);
-    if (ensure_scratch(d, need)) return 1;
-    char *sc = (char *)d->scratch;
+    // stream-ordered scratch: concurrent calls on different streams of one device do not share it
+    char *sc = nullptr;
+    WDB_CUDA(cudaMallocAsync((void **)&sc, need, stream));
     long long *d_total = (long long *)sc;
     long long *d_offs = (long long *)(sc + 64);
     long long *d_sums = (long long *)(sc + 64 + off_bytes);
@@ -159,10 +160,9 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
       }
     }
     if (d_count) WDB_CUDA(cudaMemcpyAsync(d_count, d_total, 8, cudaMemcpyDeviceToDevice, stream));
-    if (h_count) {
-      WDB_CUDA(cudaMemcpyAsync(h_count, d_total, 8, cudaMemcpyDeviceToHost, stream));
-      WDB_CUDA(cudaStreamSynchronize(stream));
-    }
+    if (h_count) WDB_CUDA(cudaMemcpyAsync(h_count, d_total, 8, cudaMemcpyDeviceToHost, stream));
+    WDB_CUDA(cudaFreeAsync(sc, stream));
+    if (h_count) WDB_CUDA(cudaStreamSynchronize(stream));
     return 0;
   }
   Kernel k;
@@ -172,8 +172,8 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
   const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
   // scratch: [0,8) survivor count, [8,12) ticket, [64, 64+8*ntiles) tile status words
   const size_t need = 64 + (size_t)std::max<int64_t>(ntiles, 1) * 8;
-  if (ensure_scratch(d, need)) return 1;
-  char *sc = (char *)d->scratch;
+  char *sc = nullptr;
+  WDB_CUDA(cudaMallocAsync((void **)&sc, need, stream));
   WDB_CUDA(cudaMemsetAsync(sc, 0, need, stream));
   long long *d_cnt = (long long *)sc;
   unsigned *d_ticket = (unsigned *)(sc + 8);
@@ -200,10 +200,9 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
     }
   }
   if (d_count) WDB_CUDA(cudaMemcpyAsync(d_count, d_cnt, 8, cudaMemcpyDeviceToDevice, stream));
-  if (h_count) {
-    WDB_CUDA(cudaMemcpyAsync(h_count, d_cnt, 8, cudaMemcpyDeviceToHost, stream));
-    WDB_CUDA(cudaStreamSynchronize(stream));
-  }
+  if (h_count) WDB_CUDA(cudaMemcpyAsync(h_count, d_cnt, 8, cudaMemcpyDeviceToHost, stream));
+  WDB_CUDA(cudaFreeAsync(sc, stream));
+  if (h_count) WDB_CUDA(cudaStreamSynchronize(stream));
   return 0;
 }
 

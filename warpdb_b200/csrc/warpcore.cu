@@ -95,20 +95,6 @@ int get_device(int id, Device **out) {
   return 0;
 }
 
-int ensure_scratch(Device *d, size_t bytes) {
-  if (bytes <= d->scratch_bytes) return 0;
-  if (d->scratch) {
-    WDB_CUDA(cudaDeviceSynchronize());
-    WDB_CUDA(cudaFree(d->scratch));
-    d->scratch = nullptr;
-    d->scratch_bytes = 0;
-  }
-  size_t want = std::max(bytes, (size_t)1 << 20);
-  WDB_CUDA(cudaMalloc(&d->scratch, want));
-  d->scratch_bytes = want;
-  return 0;
-}
-
 // ------------------------------------------------------------------------------------------------
 // code generation
 // ------------------------------------------------------------------------------------------------
@@ -542,9 +528,6 @@ int wdb_shutdown(void) {
     for (auto &kv : d->cache)
       if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
     d->cache.clear();
-    if (d->scratch) cudaFree(d->scratch);
-    d->scratch = nullptr;
-    d->scratch_bytes = 0;
     d->ready = false;
   }
   return 0;
