@@ -145,6 +145,12 @@ int main() {
     CHECK(arr.length == 4 && arr.n_buffers == 2 && std::string(sch.format) == "f" && std::string(sch.name) == "result");
     CHECK(static_cast<const float *>(arr.buffers[1])[3] == 31.0f);
     arr.release(&arr); sch.release(&sch);
+    // device-side Arrow export: the result stays in HBM
+    ArrowDeviceArray darr; ArrowSchema dsch;
+    db.query_arrow_device("price * quantity WHERE price > 10", &darr, &dsch);
+    CHECK(darr.device_type == ARROW_DEVICE_CUDA && darr.array.length == 4 && std::string(dsch.format) == "f");
+    CHECK((to_host(static_cast<const float *>(darr.array.buffers[1]), 4) == r));
+    darr.array.release(&darr.array);
     // optimizer: a condition no row can satisfy is pruned from the table statistics
     Table t = db.table();
     execute_query_optimized("price", "price > 1000", t);   // prints "[Optimizer] Filter eliminates all rows."

@@ -42,6 +42,23 @@ struct ArrowArray {
 
 #endif /* ARROW_C_DATA_INTERFACE */
 
+#ifndef ARROW_C_DEVICE_DATA_INTERFACE
+#define ARROW_C_DEVICE_DATA_INTERFACE
+/* Arrow C device data interface (https://arrow.apache.org/docs/format/CDeviceDataInterface.html) */
+typedef int32_t ArrowDeviceType;
+#define ARROW_DEVICE_CPU 1
+#define ARROW_DEVICE_CUDA 2
+#define ARROW_DEVICE_CUDA_HOST 3
+
+struct ArrowDeviceArray {
+  struct ArrowArray array;
+  int64_t device_id;
+  ArrowDeviceType device_type;
+  void *sync_event;
+  int64_t reserved[3];
+};
+#endif /* ARROW_C_DEVICE_DATA_INTERFACE */
+
 #ifdef __cplusplus
 }
 #endif

@@ -420,6 +420,54 @@ void WarpDB::query_arrow(const std::string &expr, ArrowArray *out_array, ArrowSc
   export_to_arrow(result.data(), static_cast<int64_t>(result.size()), use_shared_memory, out_array, out_schema);
 }
 
+namespace {
+struct DeviceResultOwner {
+  void *d = nullptr;
+  const void *buffers[2] = {nullptr, nullptr};
+};
+void release_device_array(ArrowArray *a) {
+  if (!a || !a->private_data) return;
+  auto *o = static_cast<DeviceResultOwner *>(a->private_data);
+  if (o->d) cudaFree(o->d);
+  delete o;
+  a->private_data = nullptr;
+  a->release = nullptr;
+}
+void release_plain_schema(ArrowSchema *s) { s->release = nullptr; }
+}  // namespace
+
+void WarpDB::query_arrow_device(const std::string &expr, ArrowDeviceArray *out_array, ArrowSchema *out_schema) {
+  if (!out_array || !out_schema) throw std::invalid_argument("Null output");
+  if (expr.empty()) throw std::runtime_error("Empty query expression");
+  std::unordered_set<std::string> cols;
+  for (const auto &c : table_.columns) cols.insert(c.name);
+  const ParsedExpr p = parse_expr_where(expr, cols, true);
+  refresh_udf_source();
+  auto *o = new DeviceResultOwner();
+  const size_t n = static_cast<size_t>(table_.num_rows);
+  if (cudaMalloc(&o->d, sizeof(float) * (n ? n : 1)) != cudaSuccess) { delete o; throw std::runtime_error("CUDA error: out of memory"); }
+  if (filter_project(p.expr_cuda, p.cond_cuda, p.cond_ast.get(), static_cast<float *>(o->d), WDB_DENSE_ZERO, nullptr)) {
+    cudaFree(o->d);
+    delete o;
+    raise_core();
+  }
+  o->buffers[1] = o->d;
+  *out_array = ArrowDeviceArray{};
+  out_array->array.length = table_.num_rows;
+  out_array->array.n_buffers = 2;
+  out_array->array.buffers = o->buffers;
+  out_array->array.release = release_device_array;
+  out_array->array.private_data = o;
+  out_array->device_id = 0;
+  out_array->device_type = ARROW_DEVICE_CUDA;
+  out_array->sync_event = nullptr;   // the producing kernel has completed (the call synchronises)
+  *out_schema = ArrowSchema{};
+  out_schema->format = "f";
+  out_schema->name = "result";
+  out_schema->flags = ARROW_FLAG_NULLABLE;
+  out_schema->release = release_plain_schema;
+}
+
 std::vector<float> WarpDB::query_multi_gpu(const std::string &expr) {
   if (host_table_.num_rows() == 0) throw std::runtime_error("Host table not available for multi-GPU query");   // :509-511
   std::unordered_set<std::string> cols;   // the reference hard-codes {"price","quantity"} (:528); the table's own columns are used

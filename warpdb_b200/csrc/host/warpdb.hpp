@@ -31,6 +31,11 @@ public:
   // query() exported through the Arrow C data interface
   void query_arrow(const std::string &expr, ArrowArray *out_array, ArrowSchema *out_schema, bool use_shared_memory = false);
 
+  // query() whose result stays in HBM, exported through the Arrow C *device* data interface
+  // (ARROW_DEVICE_CUDA): no D2H copy, buffers[1] is a device pointer owned by the array.
+  // SURVEY section 8(f) item 2; not in the reference (src/arrow_utils.cpp:37-94 copies to the host).
+  void query_arrow_device(const std::string &expr, ArrowDeviceArray *out_array, ArrowSchema *out_schema);
+
   int num_rows() const { return table_.num_rows; }
   const Table &table() const { return table_; }
 

@@ -23,7 +23,12 @@ __device__ __forceinline__ void wdb_emit_vec(float *__restrict__ out, i64 row, c
 #pragma unroll
     for (int j = 0; j < WDB_VEC; ++j) v[j] = WDB_EXPR(R, j);
     wdb_store_vec(out, row, v);
-  } else if (m) {
+  } else if (__popc(m) <= 2) {
+    // one or two survivors (the common partial vector at low selectivity): predicated 4-byte stores
+#pragma unroll
+    for (int j = 0; j < WDB_VEC; ++j)
+      if ((m >> j) & 1u) out[row + j] = WDB_EXPR(R, j);
+  } else {
 #if WDB_ALIGNED
     // partially passing vector: read-modify-write of the whole vector (one 256-bit load + store)
     // instead of up to WDB_VEC predicated 4-byte stores, which cost 2.6 ms per 1e9 rows at 50 %
