@@ -166,9 +166,9 @@ def test_kernel_variants_agree(variant, vec, unroll, block):
             wc.set_option(k, v)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_compaction_variants_agree(variant):
-    """ticket + register loads / TMA bulk ring / two-pass count-scan-scatter: identical packed output."""
+    """ticket + register loads / TMA bulk ring / two-pass count-scan-scatter / L2-parked slabs: identical packed output."""
     n = 2_000_003
     t = {"price": orc.synth_f32(n, 13, 0.0, 40.0), "quantity": orc.synth_i32(n, 14, 1, 101)}
     d = dev(t)

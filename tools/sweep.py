@@ -134,6 +134,9 @@ def sweep_compact(n):
         for vec, unroll, block in itertools.product([4, 8], [1, 2, 4], [128, 256, 512]):
             if block * vec * unroll * 4 <= 46 * 1024:
                 cfgs.append({"variant": 2, "vec": vec, "unroll": unroll, "block": block, "min_ctas": 1, "lookback": 1, "ctas_per_sm": 8})
+        for unroll, block, slab_m, minc in itertools.product([2, 4], [256, 512], [2, 4, 8], [1, 2, 3, 4]):
+            if block * 8 * unroll * 4 <= 46 * 1024 and minc * block <= 2048:
+                cfgs.append({"variant": 3, "vec": 8, "unroll": unroll, "block": block, "min_ctas": minc, "lookback": 1, "ctas_per_sm": 8, "slab_m": slab_m})
         if os.environ.get("SWEEP_ONLY_VARIANT"):
             cfgs = [c for c in cfgs if c["variant"] == int(os.environ["SWEEP_ONLY_VARIANT"])]
         for cfg in cfgs:

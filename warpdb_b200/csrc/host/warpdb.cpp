@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cctype>
 #include <fstream>
+#include <future>
 #include <memory>
 #include <stdexcept>
 #include <unordered_set>
@@ -486,13 +487,20 @@ std::vector<float> WarpDB::query_multi_gpu_csv(const std::string &csv_path, cons
   std::unordered_set<std::string> cols(names.begin(), names.end());
   const ParsedExpr p = parse_expr_where(expr, cols, false);
   refresh_udf_source();
+  // Chunk i+1 is read and parsed on a helper thread while the GPUs work on chunk i (the reference
+  // parses, uploads, runs and downloads strictly one after the other: src/warpdb.cpp:580-587).
   bool finished = false;
   std::vector<float> all;
-  while (!finished) {
-    HostTable chunk = load_csv_chunk(file, rows_per_chunk, finished, names);
-    if (chunk.num_rows() == 0) break;
+  auto read_chunk = [&]() { return load_csv_chunk(file, rows_per_chunk, finished, names); };
+  HostTable chunk = read_chunk();
+  while (chunk.num_rows() > 0) {
+    const bool last = finished;
+    std::future<HostTable> next;
+    if (!last) next = std::async(std::launch::async, read_chunk);
     const std::vector<float> part = run_multi_gpu_jit_host(chunk, p.expr_cuda, p.cond_cuda);
     all.insert(all.end(), part.begin(), part.end());
+    if (last) break;
+    chunk = next.get();
   }
   return all;
 }

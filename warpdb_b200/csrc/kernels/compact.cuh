@@ -81,7 +81,7 @@ __device__ __forceinline__ i64 wdb_lookback(const u64 *__restrict__ status, cons
   }
 }
 
-#if !WDB_BULK && !WDB_TWOPASS
+#if !WDB_BULK && !WDB_TWOPASS && !WDB_L2PASS
 // ---- variant 0: register-staged vector loads, tiles handed out in ticket order
 extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
 wdb_compact(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n,
@@ -538,5 +538,191 @@ wdb_scatter(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
       out2[g0 + i] = s_stage2[warp][i];
 #endif
     }
+}
+#endif
+
+#if WDB_L2PASS
+// ---- variant 3: single HBM pass with the tile parked in L2.  A CTA owns a slab of
+// WDB_NWARPS * WDB_SLAB_M chunks (e.g. 32 K rows = 128 KB of a float column).  Phase 1 streams the
+// slab from HBM and only counts survivors; the CTA then resolves its global offset with ONE
+// decoupled look-back per slab; phase 2 re-reads the slab -- which is still in the 126 MB L2 as long
+// as the slabs in flight (CTAs x slab bytes) fit -- ranks the survivors and writes them.  Compared
+// with the register/shared-memory single-pass kernels the look-back latency is paid once per 128 KB
+// instead of once per 32 KB and is covered by the other resident CTAs; compared with the two-pass
+// variant the second read comes from L2, not HBM.
+#ifndef WDB_SLAB_M
+#define WDB_SLAB_M 4
+#endif
+#define WDB_SLAB_CHUNKS (WDB_NWARPS * WDB_SLAB_M)
+
+__device__ __forceinline__ u32 wdb_chunk_flags(const wdb_cols &C, const i64 n, const i64 chunk, const u32 lane, const float wdb_tau,
+                                               u32 (&flags)[WDB_UNROLL], float (&vals)[WDB_UNROLL][WDB_VEC],
+#if WDB_NOUT == 2
+                                               float (&vals2)[WDB_UNROLL][WDB_VEC],
+#endif
+                                               const bool want_vals) {
+  const i64 row0 = chunk * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
+  u32 cnt = 0;
+  if ((chunk + 1) * WDB_WARP_ROWS <= n) {
+    wdb_rows R[WDB_UNROLL];
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows(C, row0 + (i64)u * WDB_SLAB_ROWS, R[u]);
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) {
+      u32 m = 0;
+#pragma unroll
+      for (int j = 0; j < WDB_VEC; ++j) {
+        m |= (WDB_KEEP(R[u], j) ? 1u : 0u) << j;
+        if (want_vals) {
+          vals[u][j] = WDB_EXPR(R[u], j);
+#if WDB_NOUT == 2
+          vals2[u][j] = WDB_EXPR2(R[u], j);
+#endif
+        }
+      }
+      flags[u] = m;
+      cnt += __popc(m);
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < WDB_UNROLL; ++u) {
+      u32 m = 0;
+#pragma unroll
+      for (int j = 0; j < WDB_VEC; ++j) {
+        const i64 row = row0 + (i64)u * WDB_SLAB_ROWS + j;
+        vals[u][j] = 0.0f;
+#if WDB_NOUT == 2
+        vals2[u][j] = 0.0f;
+#endif
+        if (row < n) {
+          wdb_rows T1;
+          wdb_load_row1(C, row, T1, 0);
+          if (WDB_KEEP(T1, 0)) {
+            m |= 1u << j;
+            vals[u][j] = WDB_EXPR(T1, 0);
+#if WDB_NOUT == 2
+            vals2[u][j] = WDB_EXPR2(T1, 0);
+#endif
+          }
+        }
+      }
+      flags[u] = m;
+      cnt += __popc(m);
+    }
+  }
+  return cnt;   // this lane's survivors in the chunk
+}
+
+extern "C" __global__ void __launch_bounds__(WDB_BLOCK, WDB_MIN_CTAS)
+wdb_compact_l2(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n,
+               u64 *__restrict__ status, u32 *__restrict__ ticket, i64 *__restrict__ out_count, const i64 nslabs,
+               const i64 nchunks, const float wdb_tau, const i64 out_cap) {
+  __shared__ float s_stage[WDB_NWARPS][WDB_WARP_ROWS];
+#if WDB_NOUT == 2
+  __shared__ float s_stage2[WDB_NWARPS][WDB_WARP_ROWS];
+#endif
+  __shared__ u32 s_wcount[WDB_NWARPS];
+  __shared__ i64 s_base;
+  __shared__ u32 s_slab;
+  const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const u32 lt = wdb_lanemask_lt();
+  while (true) {
+    if (threadIdx.x == 0) s_slab = atomicAdd(ticket, 1u);
+    __syncthreads();                                            // (1)
+    const i64 slab = (i64)s_slab;
+    if (slab >= nslabs) break;
+    const i64 chunk0 = slab * WDB_SLAB_CHUNKS + (i64)warp * WDB_SLAB_M;
+    u32 flags[WDB_UNROLL];
+    float vals[WDB_UNROLL][WDB_VEC];
+#if WDB_NOUT == 2
+    float vals2[WDB_UNROLL][WDB_VEC];
+#endif
+    // phase 1: count (HBM -> L2)
+    u32 ccount[WDB_SLAB_M];
+    u32 wtotal = 0;
+#pragma unroll
+    for (int m = 0; m < WDB_SLAB_M; ++m) {
+      u32 c = 0;
+      if (chunk0 + m < nchunks) {
+#if WDB_NOUT == 2
+        c = wdb_chunk_flags(C, n, chunk0 + m, lane, wdb_tau, flags, vals, vals2, false);
+#else
+        c = wdb_chunk_flags(C, n, chunk0 + m, lane, wdb_tau, flags, vals, false);
+#endif
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(WDB_FULL_MASK, c, o);
+      ccount[m] = c;
+      wtotal += c;
+    }
+    if (lane == 0) s_wcount[warp] = wtotal;
+    __syncthreads();                                            // (2)
+    u32 woff = 0, ttotal = 0;
+#pragma unroll
+    for (int w = 0; w < WDB_NWARPS; ++w) {
+      const u32 c = s_wcount[w];
+      woff += (w < (int)warp) ? c : 0u;
+      ttotal += c;
+    }
+    if (warp == 0) {
+      i64 excl = 0;
+      if (slab == 0) {
+        if (lane == 0) wdb_st_status(&status[0], (WDB_ST_PREFIX << 62) | (u64)ttotal);
+      } else {
+        if (lane == 0) wdb_st_status(&status[slab], (WDB_ST_AGG << 62) | (u64)ttotal);
+        excl = wdb_lookback(status, slab, lane);
+        if (lane == 0) wdb_st_status(&status[slab], (WDB_ST_PREFIX << 62) | (u64)(excl + (i64)ttotal));
+      }
+      if (lane == 0) {
+        s_base = excl;
+        if (slab == nslabs - 1) *out_count = excl + (i64)ttotal;
+      }
+    }
+    __syncthreads();                                            // (3)
+    // phase 2: re-read (L2), rank, stage per warp, write
+    i64 g0 = s_base + (i64)woff;
+#pragma unroll
+    for (int m = 0; m < WDB_SLAB_M; ++m) {
+      if (chunk0 + m >= nchunks || ccount[m] == 0u) continue;   // warp-uniform
+#if WDB_NOUT == 2
+      wdb_chunk_flags(C, n, chunk0 + m, lane, wdb_tau, flags, vals, vals2, true);
+#else
+      wdb_chunk_flags(C, n, chunk0 + m, lane, wdb_tau, flags, vals, true);
+#endif
+      u32 total = 0;
+#pragma unroll
+      for (int u = 0; u < WDB_UNROLL; ++u) {
+        u32 pre = 0, tot = 0;
+#pragma unroll
+        for (int j = 0; j < WDB_VEC; ++j) {
+          const u32 b = __ballot_sync(WDB_FULL_MASK, (flags[u] >> j) & 1u);
+          pre += __popc(b & lt);
+          tot += __popc(b);
+        }
+        u32 pos = total + pre;
+#pragma unroll
+        for (int j = 0; j < WDB_VEC; ++j)
+          if ((flags[u] >> j) & 1u) {
+            s_stage[warp][pos] = vals[u][j];
+#if WDB_NOUT == 2
+            s_stage2[warp][pos] = vals2[u][j];
+#endif
+            ++pos;
+          }
+        total += tot;
+      }
+      __syncwarp();
+      const int mis = (int)(g0 & 31);
+      for (int i = (int)lane - mis; i < (int)total; i += 32)
+        if (i >= 0 && g0 + i < out_cap) {
+          out[g0 + i] = s_stage[warp][i];
+#if WDB_NOUT == 2
+          out2[g0 + i] = s_stage2[warp][i];
+#endif
+        }
+      __syncwarp();
+      g0 += total;
+    }
+  }
 }
 #endif

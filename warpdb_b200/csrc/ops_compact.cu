@@ -94,7 +94,8 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
   spec.defines = {{"WDB_VEC", vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("compact.ld_hint", 0)},
                   {"WDB_ST_HINT", 0}, {"WDB_BLOCK", block}, {"WDB_UNROLL", unroll}, {"WDB_NOUT", two ? 2 : 1},
                   {"WDB_THRESH", two ? thresh : 0}, {"WDB_MIN_CTAS", opt("compact.min_ctas", 1)},
-                  {"WDB_LB", opt("compact.lookback", variant == 1 ? 4 : 1)}, {"WDB_BULK", variant == 1 ? 1 : 0}, {"WDB_TWOPASS", variant == 2 ? 1 : 0}, {"WDB_PRUNE", prune ? 1 : 0}};
+                  {"WDB_LB", opt("compact.lookback", variant == 1 ? 4 : 1)}, {"WDB_BULK", variant == 1 ? 1 : 0}, {"WDB_TWOPASS", variant == 2 ? 1 : 0}, {"WDB_PRUNE", prune ? 1 : 0},
+                  {"WDB_L2PASS", variant == 3 ? 1 : 0}, {"WDB_SLAB_M", opt("compact.slab_m", 4)}};
   if (variant == 1) spec.defines.push_back({"WDB_TILE", p->tile_rows});
   spec.fns.push_back({"expr", "float", expr});
   if (two) spec.fns.push_back({"expr2", "float", expr2});
@@ -166,10 +167,12 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
     return 0;
   }
   Kernel k;
-  const bool bulk = p.variant == 1;
-  if (get_kernel(d, gen_source(spec), "wdb_compact.cu", bulk ? "wdb_compact_bulk" : "wdb_compact", &k)) return 1;
+  const bool bulk = p.variant == 1, l2pass = p.variant == 3;
+  if (get_kernel(d, gen_source(spec), "wdb_compact.cu", bulk ? "wdb_compact_bulk" : (l2pass ? "wdb_compact_l2" : "wdb_compact"), &k)) return 1;
 
-  const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
+  // variant 3 works on slabs of slab_m chunks per warp; the status words are per slab
+  const int64_t slab_rows = tile_rows * std::max<int64_t>(1, opt("compact.slab_m", 4));
+  const int64_t ntiles = l2pass ? (n + slab_rows - 1) / slab_rows : (n + tile_rows - 1) / tile_rows;
   // scratch: [0,8) survivor count, [8,12) ticket, [64, 64+8*ntiles) tile status words
   const size_t need = 64 + (size_t)std::max<int64_t>(ntiles, 1) * 8;
   char *sc = nullptr;
@@ -194,6 +197,11 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
     if (bulk) {
       void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_cnt, &nt, &tau, &cap};
       if (launch(k, grid, block, p.smem, stream, args)) return 1;
+    } else if (l2pass) {
+      const int64_t chunk_rows = tile_rows / (block / 32);
+      long long nchunks = (n + chunk_rows - 1) / chunk_rows;
+      void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_ticket, &d_cnt, &nt, &nchunks, &tau, &cap};
+      if (launch(k, grid, block, 0, stream, args)) return 1;
     } else {
       void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_ticket, &d_cnt, &nt, &tau, &cap};
       if (launch(k, grid, block, 0, stream, args)) return 1;
