@@ -66,7 +66,8 @@ int wdb_device_count(int *out);
 /* Source prepended to every generated kernel: the contents of ./custom.cu (src/jit.cpp:65-73).
  * NULL or "" clears it.  The C++ shim re-reads the file per call like the reference does. */
 int wdb_set_udf_source(const char *cuda_src);
-/* Tuning knobs ("project.variant", "project.block", "project.unroll", ...); see DESIGN.md. */
+/* Tuning knobs ("project.variant", "project.block", "project.unroll", ...); see DESIGN.md.
+ * value == INT64_MIN removes the override (built-in default). */
 int wdb_set_option(const char *key, int64_t value);
 int wdb_get_option(const char *key, int64_t *value);
 /* Statistics of the kernel cache and of the last call on this thread. */

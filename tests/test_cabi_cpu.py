@@ -58,24 +58,27 @@ def test_only_referenced_columns_are_loaded(tmp_path):
 
 
 def test_compact_kernels(tmp_path):
-    # default: two streaming passes (count -> scan -> scatter), ballot/popc ranking, no atomics, no barriers
-    _, cubin = wc.debug_compile("compact", SCHEMA, "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", wc.COMPACT)
-    sass = sass_of(cubin, tmp_path)
-    assert "wdb_count" in sass and "wdb_scatter" in sass and "VOTE" in sass and "POPC" in sass
-    assert "ATOMG" not in sass and "BAR.SYNC" not in sass and re.search(r"LDG\.E\.NA\.\w+\.256", sass)
-    try:
-        # single pass, TMA bulk-copy ring (UBLKCP + mbarrier), status-word look-back
-        wc.set_option("compact.variant", 1)
+    def sass_for(variant, name):
+        wc.set_option("compact.variant", variant)
         _, cubin = wc.debug_compile("compact", SCHEMA, "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", wc.COMPACT)
-        sass = sass_of(cubin, tmp_path, "k1.cubin")
+        return sass_of(cubin, tmp_path, name)
+    try:
+        # default: one HBM pass, slab parked in L2 (count -> one look-back per slab -> re-read, rank, write)
+        sass = sass_for(3, "k3.cubin")
+        assert "wdb_compact_l2" in sass and "VOTE" in sass and "POPC" in sass and "LDG.E.64.STRONG.GPU" in sass
+        assert re.search(r"LDG\.E\.NA\.\w+\.256", sass)
+        # two streaming passes (count -> scan -> scatter): no atomics, no block barriers
+        sass = sass_for(2, "k2.cubin")
+        assert "wdb_count" in sass and "wdb_scatter" in sass and "VOTE" in sass and "POPC" in sass
+        assert "ATOMG" not in sass and "BAR.SYNC" not in sass
+        # single pass, TMA bulk-copy ring (UBLKCP + mbarrier), status-word look-back
+        sass = sass_for(1, "k1.cubin")
         assert "wdb_compact_bulk" in sass and "UBLKCP" in sass and "SYNCS" in sass and "LDG.E.64.STRONG.GPU" in sass
         # single pass, register-staged vector loads, atomic tile ticket
-        wc.set_option("compact.variant", 0)
-        _, cubin = wc.debug_compile("compact", SCHEMA, "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", wc.COMPACT)
-        sass = sass_of(cubin, tmp_path, "k0.cubin")
+        sass = sass_for(0, "k0.cubin")
         assert "VOTE" in sass and "POPC" in sass and "ATOMG" in sass and "LDG.E.64.STRONG.GPU" in sass
     finally:
-        wc.set_option("compact.variant", 2)
+        wc.set_option("compact.variant", None)
 
 
 def test_bulk_variant_emits_tma_bulk_copies(tmp_path):
@@ -83,7 +86,7 @@ def test_bulk_variant_emits_tma_bulk_copies(tmp_path):
     try:
         _, cubin = wc.debug_compile("project", SCHEMA, "((price[idx] * quantity[idx]) * 1.08f)")
     finally:
-        wc.set_option("project.variant", 0)
+        wc.set_option("project.variant", None)
     sass = sass_of(cubin, tmp_path)
     assert "UBLKCP" in sass and "SYNCS" in sass
 

@@ -162,8 +162,8 @@ def test_kernel_variants_agree(variant, vec, unroll, block):
         out, _ = ops.project_filter(d, "(price[idx] * 0.9f)", "(price[idx] > 20.0f)", wc.DENSE_ZERO)
         assert np.array_equal(bits(out.cpu().numpy()), bits(ref0))
     finally:
-        for k, v in {"project.variant": 0, "project.vec": 8, "project.unroll": 2, "project.block": 512}.items():
-            wc.set_option(k, v)
+        for k in opts:
+            wc.set_option(k, None)
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
@@ -179,7 +179,7 @@ def test_compaction_variants_agree(variant):
             out, cnt = ops.project_filter(d, orc.Expr(text).cuda(), orc.Expr(where).cuda(), wc.COMPACT)
             assert cnt == len(ref) and np.array_equal(bits(out[:cnt].cpu().numpy()), bits(ref)), (variant, text, where)
     finally:
-        wc.set_option("compact.variant", 2)
+        wc.set_option("compact.variant", None)
 
 
 def test_compile_error_and_recovery():

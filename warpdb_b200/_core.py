@@ -117,7 +117,8 @@ def make_cols(schema):
 
 
 def set_option(key, value):
-    check(lib().wdb_set_option(key.encode(), int(value)))
+    """value=None removes the override (built-in default)."""
+    check(lib().wdb_set_option(key.encode(), -(1 << 63) if value is None else int(value)))
 
 
 def set_udf_source(src):

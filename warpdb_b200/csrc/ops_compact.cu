@@ -74,7 +74,7 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
     if (dtype_size(u.dtype) == 0) return fail("column %s has a non-numeric type and cannot be read on the GPU", u.name.c_str());
   const int block = (int)opt("compact.block", 256), vec = (int)opt("compact.vec", 8);
   int unroll = (int)opt("compact.unroll", 4);
-  int variant = (int)opt("compact.variant", 2);   // default from profiles/r01_sweep_compact_*.jsonl   // 0 ticket + register loads, 1 TMA bulk ring, 2 two-pass count/scatter
+  int variant = (int)opt("compact.variant", two ? 2 : 3);   // defaults from profiles/r01_sweep_compact_*.jsonl   // 0 ticket + register loads, 1 TMA bulk ring, 2 two-pass count/scatter
   if (vec != 4 && vec != 8) return fail("compact.vec must be 4 or 8");
   if (block < 32 || block > 1024 || (block & 31)) return fail("compact.block must be a multiple of 32 in [32,1024]");
   if (unroll < 1 || unroll > 8) return fail("compact.unroll must be in [1,8]");
@@ -93,7 +93,7 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
   if (variant != 1 && p->tile_rows * 4 * (two ? 2 : 1) > 46 * 1024) return fail("compact tile of %lld rows does not fit static shared memory", (long long)p->tile_rows);
   spec.defines = {{"WDB_VEC", vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("compact.ld_hint", 0)},
                   {"WDB_ST_HINT", 0}, {"WDB_BLOCK", block}, {"WDB_UNROLL", unroll}, {"WDB_NOUT", two ? 2 : 1},
-                  {"WDB_THRESH", two ? thresh : 0}, {"WDB_MIN_CTAS", opt("compact.min_ctas", 1)},
+                  {"WDB_THRESH", two ? thresh : 0}, {"WDB_MIN_CTAS", opt("compact.min_ctas", variant == 3 ? 4 : 1)},
                   {"WDB_LB", opt("compact.lookback", variant == 1 ? 4 : 1)}, {"WDB_BULK", variant == 1 ? 1 : 0}, {"WDB_TWOPASS", variant == 2 ? 1 : 0}, {"WDB_PRUNE", prune ? 1 : 0},
                   {"WDB_L2PASS", variant == 3 ? 1 : 0}, {"WDB_SLAB_M", opt("compact.slab_m", 4)}};
   if (variant == 1) spec.defines.push_back({"WDB_TILE", p->tile_rows});

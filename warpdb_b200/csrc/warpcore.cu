@@ -547,7 +547,8 @@ int wdb_set_udf_source(const char *src) {
 int wdb_set_option(const char *key, int64_t value) {
   if (!key) return fail("null option key");
   std::lock_guard<std::mutex> l(g_mu);
-  g_opts[key] = value;
+  if (value == INT64_MIN) g_opts.erase(key);   // back to the built-in default
+  else g_opts[key] = value;
   return 0;
 }
 int wdb_get_option(const char *key, int64_t *value) {
