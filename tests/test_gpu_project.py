@@ -199,3 +199,29 @@ def test_kernel_cache_hits():
     s1 = wc.stats()
     assert s1["kernels_compiled"] == s0["kernels_compiled"] and s1["cache_hits"] == s0["cache_hits"] + 1
     assert s1["launches"] > s0["launches"]
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("n", [1, 1023, 8192, 8193, 40_001, 1_000_001])
+def test_no_writes_outside_the_output(variant, n):
+    """compute-sanitizer is closed on this pool: guard regions around the output buffer instead.  The
+    output slice starts 32-byte aligned inside a larger tensor filled with a sentinel; nothing outside
+    [0, n) (dense) or [0, count) (compact) may change."""
+    GUARD, S = 4096, -12345.0
+    t = {"price": orc.synth_f32(n, 15, 0.0, 40.0), "quantity": orc.synth_i32(n, 16, 1, 101)}
+    d = dev(t)
+    try:
+        wc.set_option("compact.variant", variant)
+        for mode in (wc.DENSE, wc.DENSE_ZERO, wc.COMPACT):
+            buf = torch.full((n + 2 * GUARD,), S, dtype=torch.float32, device="cuda")
+            out = buf[GUARD:GUARD + n]
+            _, cnt = ops.project_filter(d, "(price[idx] * 0.9f)", "(price[idx] > 20.0f)", mode, out=out)
+            h = buf.cpu().numpy()
+            assert (h[:GUARD] == S).all() and (h[GUARD + n:] == S).all(), (variant, n, mode)
+            if mode == wc.COMPACT:
+                assert (h[GUARD + cnt:GUARD + n] == S).all(), (variant, n, "compact tail")
+            elif mode == wc.DENSE:
+                keep = t["price"] > np.float32(20)
+                assert (h[GUARD:GUARD + n][~keep] == S).all(), (variant, n, "untouched slots")
+    finally:
+        wc.set_option("compact.variant", None)

@@ -8,6 +8,7 @@
 // launches and downloads one device after the other with synchronous copies).
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <thread>
 
 #include "core.hpp"
@@ -39,8 +40,22 @@ static int run_shard(ShardJob *job, const wdb_col_t *h_cols, int ncols, const ch
   const int nslots = (int)std::max<int64_t>(1, std::min<int64_t>(opt("multi.slots", 2), (rows + chunk - 1) / chunk));
   size_t row_bytes = 4;
   for (const auto &u : used) row_bytes += dtype_size(u.dtype);
-  char *pool = nullptr;
-  WDB_CUDA(cudaMalloc((void **)&pool, (size_t)nslots * (size_t)chunk * row_bytes + 256 * (used.size() + 2) * nslots));
+  // the ring of device buffers is kept per device across calls (cudaMalloc/cudaFree of a multi-GB
+  // ring cost 50-250 ms per call and made the end-to-end time erratic); one host-buffer call per
+  // device at a time
+  static std::mutex ring_mu[64];
+  static char *ring_ptr[64];
+  static size_t ring_bytes[64];
+  std::lock_guard<std::mutex> ring_lock(ring_mu[job->dev]);
+  const size_t need = (size_t)nslots * (size_t)chunk * row_bytes + 256 * (used.size() + 2) * nslots;
+  if (need > ring_bytes[job->dev]) {
+    if (ring_ptr[job->dev]) cudaFree(ring_ptr[job->dev]);
+    ring_ptr[job->dev] = nullptr;
+    ring_bytes[job->dev] = 0;
+    WDB_CUDA(cudaMalloc((void **)&ring_ptr[job->dev], need));
+    ring_bytes[job->dev] = need;
+  }
+  char *pool = ring_ptr[job->dev];
   std::vector<cudaStream_t> streams(nslots);
   for (auto &s : streams) WDB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   // carve: per slot, one buffer per used column (256-byte aligned) + the output
@@ -91,7 +106,6 @@ static int run_shard(ShardJob *job, const wdb_col_t *h_cols, int ncols, const ch
     if (e != cudaSuccess && !rc) rc = fail("CUDA error: %s (stream sync)", cudaGetErrorString(e));
     cudaStreamDestroy(s);
   }
-  cudaFree(pool);
   job->count = written;
   return rc;
 }
