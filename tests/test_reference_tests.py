@@ -1,0 +1,44 @@
+"""The reference's OWN test programs (/root/reference/tests/*.cpp), compiled unmodified against the
+product's host headers and libraries by `make -C oracle ref_tests` (binaries under oracle/_ref/ref_tests,
+which travel to the GPU box).  CPU: the nine front-end tests.  GPU: jit_arch_test, jit_error_test,
+extended_types_test, having_distinct_test (run from tests/, which holds data/test.csv etc.)."""
+import os
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BIN = os.path.join(ROOT, "oracle", "_ref", "ref_tests")
+
+CPU_TESTS = {"test_expression": "All parser tests passed", "expression_tests": "All tests passed",
+             "tokenizer_tests": "All tokenizer tests passed", "precedence_tests": "All precedence tests passed",
+             "query_parser_test": "Query parse test passed", "parsing_error_tests": "All regression tests passed",
+             "parse_query_error_test": "parse_query_error_test passed", "tokenize_error_test": "tokenize_error_test passed",
+             "identifier_validation_test": "identifier_validation_test passed"}
+GPU_TESTS = {"jit_arch_test": "Architecture detection test passed", "jit_error_test": "RAII test passed",
+             "extended_types_test": "extended types test passed", "having_distinct_test": "HAVING/DISTINCT tests passed"}
+
+
+@pytest.fixture(scope="module")
+def binaries():
+    if os.path.isdir("/root/reference/tests"):
+        from warpdb_b200 import build as wbuild
+        wbuild.build_host()
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref_tests"], check=True, capture_output=True)
+    if not os.path.isdir(BIN):
+        pytest.skip("oracle/_ref/ref_tests not built (needs /root/reference)")
+    return BIN
+
+
+@pytest.mark.parametrize("name", sorted(CPU_TESTS))
+def test_reference_frontend_test_program(binaries, name):
+    r = subprocess.run([os.path.join(binaries, name)], cwd=HERE, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and CPU_TESTS[name] in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(GPU_TESTS))
+def test_reference_gpu_test_program(binaries, name):
+    r = subprocess.run([os.path.join(binaries, name)], cwd=HERE, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and GPU_TESTS[name] in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]

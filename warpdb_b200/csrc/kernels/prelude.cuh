@@ -18,6 +18,10 @@ struct wdb_idx_t {};
 template <class T> struct wdb_cell {
   T v;
   __device__ __forceinline__ T &operator[](wdb_idx_t) { return v; }
+  // a bare column name denotes the current row's value too: the reference's own JIT tests pass
+  // "price" and "price + 1" as expression code (tests/jit_arch_test.cpp:23, jit_error_test.cpp:28),
+  // which its kernel text would reject (a float* assigned to a float)
+  __device__ __forceinline__ operator T() const { return v; }
 };
 
 #define WDB_FULL_MASK 0xffffffffu
