@@ -84,8 +84,6 @@ __global__ void __launch_bounds__(kSortBlock) sort_scatter_kernel(const K *__res
       unsigned run = 0;
 #pragma unroll
       for (int w = 0; w < kSortWarps; ++w) { const unsigned c = s_wcount[w][threadIdx.x]; s_wcount[w][threadIdx.x] = run; run += c; }
-      // stash the round total in the high half so the base can be advanced after use
-      s_wcount[0][threadIdx.x] |= 0;  // (kept for clarity)
       __syncthreads();
       if (valid) {
         const long long pos = s_base[d] + s_wcount[warp][d] + rank;
@@ -183,6 +181,7 @@ template int radix_sort<unsigned long long>(Device *, cudaStream_t, unsigned lon
 // sort floats in place (optionally carrying a float payload that is permuted alongside)
 int sort_f32(Device *d, cudaStream_t s, float *d_keys, float *d_payload, long long n, bool ascending) {
   if (n <= 1) return 0;
+  if (d_payload && n >= (1ll << 32)) return fail("ORDER BY with a separate SELECT expression is limited to 2^32 surviving rows (%lld given)", n);
   const size_t nb = sizeof(unsigned) * (size_t)n;
   char *buf = nullptr;
   WDB_CUDA(cudaMallocAsync((void **)&buf, nb * (d_payload ? 5 : 2), s));

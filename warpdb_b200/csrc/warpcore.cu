@@ -114,13 +114,6 @@ static const char *dtype_cuda(int dtype) {  // src/jit.cpp:31-45
   }
   return "void*";
 }
-static bool is_c_identifier(const std::string &s) {
-  if (s.empty() || !(isalpha((unsigned char)s[0]) || s[0] == '_')) return false;
-  for (char c : s)
-    if (!(isalnum((unsigned char)c) || c == '_')) return false;
-  return true;
-}
-
 // A column is read only if one of the expression strings names it (the reference passes every
 // column of the table as a kernel parameter: src/jit.cpp:75-79).
 std::vector<UsedCol> find_used_columns(const wdb_col_t *cols, int ncols, const std::vector<std::string> &texts) {
