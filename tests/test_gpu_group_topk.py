@@ -76,6 +76,35 @@ def test_group_by_where_expressions_and_unknown_cardinality():
     assert k.cpu().tolist() == ref["keys"].tolist() == [1, -1, 2147483647, -2147483648, 2]
 
 
+
+
+@pytest.mark.parametrize("opts", [{}, {"group.wp_ilp": 1}, {"group.wp_ilp": 4, "group.wp_unroll": 1}, {"group.wp_slots": 64, "group.wp_probes": 4},
+                                  {"group.wp_slots": 0}])
+def test_warp_private_tables_any_key_distribution(opts):
+    """Small-cardinality kernel (warp-private tables, tag arbitration): sparse/negative/sentinel keys,
+    heavy same-key conflicts inside a warp, a WHERE clause, tables too small for the key set (rows
+    spill to the global table) -- all identical to the oracle, and to the shared-atomic kernel (wp_slots 0)."""
+    for k, v in opts.items():
+        wc.set_option(k, v)
+    try:
+        n = 700_003
+        rng = np.random.default_rng(7)
+        pool = np.concatenate([rng.integers(-2**31, 2**31, 890, dtype=np.int64), [-2**31, 2**31 - 1, 0, -1, 1024, 2048, 4096, 1 << 20]]).astype(np.int32)
+        for keys in (pool[rng.integers(0, len(pool), n)], pool[:3][rng.integers(0, 3, n)], (np.arange(n) // 5000).astype(np.int32) * 1024):
+            t = {"price": orc.synth_f32(n, 91, -10.0, 100.0), "quantity": np.ascontiguousarray(keys, dtype=np.int32)}
+            for agg, cond in ((wc.SUM, None), (wc.AVG, "price > 20"), (wc.COUNT, "price > 95")):
+                ref = orc.group_agg("price", "quantity", cond, t, agg=agg)
+                k, v = ops.group_agg(dev(t), "price[idx]", "quantity[idx]", cu(cond), agg=agg, expected_groups=900)
+                assert np.array_equal(k.cpu().numpy(), ref["keys"])
+                if agg == wc.COUNT:
+                    assert np.array_equal(bits(v.cpu().numpy()), bits(ref["vals"]))
+                else:
+                    np.testing.assert_allclose(v.cpu().numpy(), ref["vals"], rtol=SUM_RTOL, atol=0)
+    finally:
+        for k in opts:
+            wc.set_option(k, None)
+
+
 def test_table_overflow_is_reported_and_retried():
     n = 300_000
     t = {"price": orc.synth_f32(n, 41, 0.0, 1.0), "quantity": np.arange(n, dtype=np.int32)}

@@ -137,7 +137,10 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   const int64_t expected = cap_hint / 2;                     // cap_hint = table capacity = 2 x expected groups
   int64_t wp = opt("group.wp_slots", -1);
   const bool wp_ok = (needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0;
-  if (wp < 0) wp = 0;   // measured 3-4x slower than the atomic path on B200 (profiles/r01_diag_group_*.jsonl); opt-in only
+  if (wp < 0) {   // auto: warp-private tables while a table of 2 x expected slots leaves room for >= 7 warps per SM
+    wp = 0;
+    if (expected <= 1024) { wp = 1024; while (wp < 2 * expected) wp <<= 1; }
+  }
   if (!wp_ok) wp = 0;
   if (wp & (wp - 1)) return fail("group.wp_slots must be a power of two");
   int64_t slots = opt("group.smem_slots", -1);
@@ -146,14 +149,17 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
     if (expected <= 2048) { slots = 1024; while (slots < 8 * expected && slots < 8192) slots <<= 1; }   // low load factor: short probe chains
   }
   if (slots & (slots - 1)) return fail("group.smem_slots must be a power of two");
+  int wp_ilp = 1;
   if (wp > 0) {
     slots = 0;
-    const size_t per_slot = 8 + 4 + 1 + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0);
-    int warps = (int)std::min<int64_t>(opt("group.wp_warps", 8), (int64_t)(200 * 1024 / (per_slot * wp)));
+    const size_t per_slot = 16 + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0);
+    int warps = (int)std::min<int64_t>(opt("group.wp_warps", 16), (int64_t)(232448 / (per_slot * wp)));
     if (warps < 1) return fail("group.wp_slots too large for shared memory");
     p->block = 32 * warps;
-    p->unroll = (int)opt("group.wp_unroll", 4);
+    p->unroll = (int)opt("group.wp_unroll", 2);
     p->vec = (int)opt("group.wp_vec", 8);
+    wp_ilp = (int)opt("group.wp_ilp", 2);
+    if (wp_ilp != 1 && wp_ilp != 2 && wp_ilp != 4) return fail("group.wp_ilp must be 1, 2 or 4");
     p->smem_bytes = per_slot * (size_t)wp * warps;
     p->entry = "wdb_group_wp";
   } else {
@@ -173,7 +179,7 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   spec.defines = {{"WDB_VEC", p->vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("group.ld_hint", 0)}, {"WDB_ST_HINT", 0},
                   {"WDB_BLOCK", p->block}, {"WDB_UNROLL", p->unroll}, {"WDB_NEEDS", needs}, {"WDB_SMEM_SLOTS", slots},
                   {"WDB_SMEM_LOG2", log2}, {"WDB_SMEM_PROBES", opt("group.smem_probes", 4)}, {"WDB_HAS_COND", has_cond ? 1 : 0},
-                  {"WDB_WP_SLOTS", wp}, {"WDB_WP_LOG2", wplog2}, {"WDB_WP_PROBES", opt("group.wp_probes", 16)}};
+                  {"WDB_WP_SLOTS", wp}, {"WDB_WP_LOG2", wplog2}, {"WDB_WP_PROBES", opt("group.wp_probes", 16)}, {"WDB_WP_ILP", wp_ilp}};
   spec.fns.push_back({"val", "float", (needs & ~WDB_NEED_CNT_BIT & ~WDB_NEED_FIRST_BIT) ? val : "0.0f"});  // COUNT never evaluates its argument (src/warpdb.cpp:376)
   spec.fns.push_back({"key", "int", key});
   if (has_cond) spec.fns.push_back({"cond", "bool", cond});
