@@ -184,7 +184,8 @@ def make_workload(name, rows, rank, world, local):
                 dist.all_reduce(tot)
             g = res["g"]
             return bool(g["keys"].numel() == G and abs(g["vals"].double().sum().item() / tot.item() - 1.0) < 1e-6)
-        return dict(step=step, bytes_per_row=8.0, kernel="wdb_group", table=table, query="SELECT SUM(price) FROM t GROUP BY quantity",
+        return dict(step=step, bytes_per_row=8.0, kernel="wdb_group_wp" if G <= 4096 else "wdb_group", table=table,
+                    query="SELECT SUM(price) FROM t GROUP BY quantity",
                     groups=G, check=check)
     if name == "topk5":
         from warpdb_b200.sharded import ShardedDB

@@ -99,6 +99,11 @@ enum { WDB_NEED_SUM = 1, WDB_NEED_COUNT = 2, WDB_NEED_MINMAX = 4, WDB_NEED_FIRST
 int wdb_agg_create(int device, int64_t expected_groups, int needs, wdb_agg_t **out);
 int wdb_agg_destroy(wdb_agg_t *t);
 int wdb_agg_reset(wdb_agg_t *t, void *stream);
+/* Optimizer statistics (TableStats, include/csv_loader.hpp:22-37; the reference never fills them,
+ * src/optimizer.cpp:13-17): every key the next consume calls will produce lies in [lo, hi] (e.g.
+ * wdb_column_minmax of the GROUP BY column).  A small span selects direct-indexed accumulators;
+ * keys outside the range stay correct (they take the general path).  known = 0 forgets the range. */
+int wdb_agg_set_key_range(wdb_agg_t *t, int known, int64_t lo, int64_t hi);
 /* fold n rows into the table (cond "" = none).  row_base is the global index of row 0 (first-appearance order). */
 int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols, const char *val_expr,
                     const char *key_expr, const char *cond, int64_t n, int64_t row_base);
@@ -108,6 +113,9 @@ int wdb_agg_merge(wdb_agg_t *t, void *stream, const int32_t *d_keys, const doubl
                   const int64_t *d_first, int64_t m);
 /* number of groups (synchronises) */
 int wdb_agg_size(wdb_agg_t *t, void *stream, int64_t *h_groups);
+/* tuning statistic: rows (mod 2^32) since the last reset that the small-cardinality kernel could not
+ * keep in its shared-memory accumulators and folded straight into the global table */
+int wdb_agg_spilled(wdb_agg_t *t, void *stream, int64_t *h_rows);
 /* export groups in `order`; any output pointer may be NULL.  d_vals holds float(agg result)
  * per src/warpdb.cpp:429-435.  cap = capacity of the output arrays.  Synchronises. */
 int wdb_agg_export(wdb_agg_t *t, void *stream, int agg, int order, int32_t *d_keys, float *d_vals,

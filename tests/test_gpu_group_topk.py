@@ -78,31 +78,60 @@ def test_group_by_where_expressions_and_unknown_cardinality():
 
 
 
-@pytest.mark.parametrize("opts", [{}, {"group.wp_ilp": 1}, {"group.wp_ilp": 4, "group.wp_unroll": 1}, {"group.wp_slots": 64, "group.wp_probes": 4},
-                                  {"group.wp_slots": 0}])
-def test_warp_private_tables_any_key_distribution(opts):
-    """Small-cardinality kernel (warp-private tables, tag arbitration): sparse/negative/sentinel keys,
-    heavy same-key conflicts inside a warp, a WHERE clause, tables too small for the key set (rows
-    spill to the global table) -- all identical to the oracle, and to the shared-atomic kernel (wp_slots 0)."""
+@pytest.mark.parametrize("opts", [{}, {"group.wp_ilp": 2}, {"group.wp_ilp": 4, "group.wp_unroll": 1}, {"group.wp_warps": 3, "group.wp_vec": 4},
+                                  {"group.wp_max_span": 0}])
+def test_warp_private_accumulators_any_key_distribution(opts):
+    """Small-cardinality kernel (warp-private direct-indexed accumulators, tag arbitration; selected
+    from the key column's min/max, gathered automatically): heavy same-key conflicts inside a warp,
+    negative keys, ranges touching INT_MIN (the table's empty sentinel) and INT_MAX, a WHERE clause --
+    all identical to the oracle and to the shared-atomic kernel (wp_max_span 0); sparse keys fall
+    back to the atomic kernel."""
+    wc.set_option("group.auto_stats_min_rows", 0)
     for k, v in opts.items():
         wc.set_option(k, v)
     try:
         n = 700_003
         rng = np.random.default_rng(7)
-        pool = np.concatenate([rng.integers(-2**31, 2**31, 890, dtype=np.int64), [-2**31, 2**31 - 1, 0, -1, 1024, 2048, 4096, 1 << 20]]).astype(np.int32)
-        for keys in (pool[rng.integers(0, len(pool), n)], pool[:3][rng.integers(0, 3, n)], (np.arange(n) // 5000).astype(np.int32) * 1024):
+        pool = np.concatenate([rng.integers(-2**31, 2**31, 890, dtype=np.int64), [-2**31, 2**31 - 1, 0, -1, 1024, 2048, 4096, 1 << 20]])
+        for keys in (pool[rng.integers(0, len(pool), n)], rng.integers(-1, 2, n), rng.integers(-1000, 1000, n),
+                     -2**31 + rng.integers(0, 900, n), 2**31 - 1 - rng.integers(0, 1500, n)):
             t = {"price": orc.synth_f32(n, 91, -10.0, 100.0), "quantity": np.ascontiguousarray(keys, dtype=np.int32)}
             for agg, cond in ((wc.SUM, None), (wc.AVG, "price > 20"), (wc.COUNT, "price > 95")):
                 ref = orc.group_agg("price", "quantity", cond, t, agg=agg)
-                k, v = ops.group_agg(dev(t), "price[idx]", "quantity[idx]", cu(cond), agg=agg, expected_groups=900)
+                k, v = ops.group_agg(dev(t), "price[idx]", "quantity[idx]", cu(cond), agg=agg, expected_groups=2000)
                 assert np.array_equal(k.cpu().numpy(), ref["keys"])
                 if agg == wc.COUNT:
                     assert np.array_equal(bits(v.cpu().numpy()), bits(ref["vals"]))
                 else:
                     np.testing.assert_allclose(v.cpu().numpy(), ref["vals"], rtol=SUM_RTOL, atol=0)
     finally:
+        wc.set_option("group.auto_stats_min_rows", None)
         for k in opts:
             wc.set_option(k, None)
+
+
+@pytest.mark.parametrize("lo,hi", [(0, 999), (-500, 1200), (100, 300), (-2**31, -2**31 + 1500), (2**31 - 900, 2**31 - 1), (0, 5000)])
+def test_key_range_statistics_select_direct_indexing_and_stay_correct_when_wrong(lo, hi):
+    """wdb_agg_set_key_range: a small [lo, hi] makes the kernel index its accumulators with key - lo;
+    keys outside the promised range (stale statistics) must still be aggregated correctly."""
+    n = 400_003
+    base = {"price": orc.synth_f32(n, 95, 0.0, 100.0)}
+    for klo, khi in ((0, 1000), (lo, min(hi + 1, 2**31 - 1) if hi < 2**31 - 1 else hi)):
+        q = (orc.synth_i32(n, 96, 0, 1000).astype(np.int64) * max((khi - klo) // 1000, 1) + klo).clip(-2**31, 2**31 - 1).astype(np.int32)
+        t = dict(base, quantity=q)
+        ref = orc.group_agg("price", "quantity", None, t, agg=orc.AVG)
+        tab = ops.AggTable(0, 1000, wc.NEED_SUM | wc.NEED_COUNT)
+        tab.set_key_range(lo, hi)
+        d = dev(t)
+        half = n // 2 // 8 * 8
+        tab.consume({k: v[:half] for k, v in d.items()}, "price[idx]", "quantity[idx]")
+        tab.set_key_range(None, None)                                   # second chunk: statistics gathered by the core, or the atomic kernel
+        tab.consume({k: v[half:] for k, v in d.items()}, "price[idx]", "quantity[idx]", row_base=half)
+        out = tab.export(wc.AVG, wc.ORDER_KEY_ASC)
+        tab.close()
+        assert np.array_equal(out["keys"].cpu().numpy(), ref["keys"])
+        assert np.array_equal(out["counts"].cpu().numpy(), ref["counts"])
+        np.testing.assert_allclose(out["sums"].cpu().numpy(), ref["sums"], rtol=1e-12)
 
 
 def test_table_overflow_is_reported_and_retried():

@@ -21,7 +21,7 @@ NEED_SUM, NEED_COUNT, NEED_MINMAX, NEED_FIRST_ROW = 1, 2, 4, 8
 SYMBOLS = [
     "wdb_abi_version", "wdb_last_error", "wdb_init", "wdb_shutdown", "wdb_device_count", "wdb_set_udf_source",
     "wdb_set_option", "wdb_get_option", "wdb_get_stats", "wdb_project_filter", "wdb_agg_create", "wdb_agg_destroy",
-    "wdb_agg_reset", "wdb_agg_consume", "wdb_agg_merge", "wdb_agg_size", "wdb_agg_export", "wdb_group_agg",
+    "wdb_agg_reset", "wdb_agg_set_key_range", "wdb_agg_consume", "wdb_agg_merge", "wdb_agg_size", "wdb_agg_spilled", "wdb_agg_export", "wdb_group_agg",
     "wdb_topk", "wdb_sort_float", "wdb_sort_pairs", "wdb_column_minmax", "wdb_multi_project_filter_host",
     "wdb_zonemap_build", "wdb_zonemap_destroy", "wdb_zonemap_info", "wdb_project_filter_pruned",
     "wdb_shard_range", "wdb_synth_f32", "wdb_synth_i32", "wdb_debug_compile", "wdb_free",
@@ -73,9 +73,11 @@ def lib():
     L.wdb_agg_create.argtypes = [ci, i64, ci, C.POINTER(vp)]
     L.wdb_agg_destroy.argtypes = [vp]
     L.wdb_agg_reset.argtypes = [vp, vp]
+    L.wdb_agg_set_key_range.argtypes = [vp, ci, i64, i64]
     L.wdb_agg_consume.argtypes = [vp, vp, PC, ci, cp, cp, cp, i64, i64]
     L.wdb_agg_merge.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64]
     L.wdb_agg_size.argtypes = [vp, vp, P64]
+    L.wdb_agg_spilled.argtypes = [vp, vp, P64]
     L.wdb_agg_export.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, i64, P64]
     L.wdb_group_agg.argtypes = [ci, vp, PC, ci, cp, cp, cp, ci, ci, i64, i64, vp, vp, i64, P64]
     L.wdb_topk.argtypes = [ci, vp, PC, ci, cp, cp, cp, ci, i64, i64, i64, vp, vp, P64]

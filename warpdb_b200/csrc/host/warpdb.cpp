@@ -347,10 +347,31 @@ std::vector<float> WarpDB::query_sql(const std::string &sql) {
     // key in the requested direction whatever its expression is (jit_sort_pairs, :370-371)
     const int order = (ast.order_by && !ast.order_by->ascending) ? WDB_ORDER_KEY_DESC : WDB_ORDER_KEY_ASC;
     int64_t expect = 1 << 16, groups = 0;
+    // optimizer statistics (TableStats): GROUP BY on a bare integer column -> its min/max bounds the
+    // number of groups and lets the core index its accumulators directly (cached per column)
+    bool have_range = false;
+    int64_t key_lo = 0, key_hi = -1;
+    if (const auto *kv = dynamic_cast<const VariableNode *>(ast.group_by->keys[0].get())) {
+      for (const auto &c : table_.columns) {
+        if (c.name != kv->name || c.type != DataType::Int32 || !c.device_ptr || n == 0) continue;
+        auto it = key_ranges_.find(c.name);
+        if (it == key_ranges_.end()) {
+          const wdb_col_t col{c.name.c_str(), static_cast<int>(c.type), c.device_ptr, n};
+          double lo = 0, hi = 0;
+          if (wdb_column_minmax(0, nullptr, &col, &lo, &hi)) raise_core();
+          it = key_ranges_.emplace(c.name, std::make_pair(static_cast<long long>(lo), static_cast<long long>(hi))).first;
+        }
+        have_range = true;
+        key_lo = it->second.first;
+        key_hi = it->second.second;
+        expect = std::min<int64_t>(expect, std::max<int64_t>(key_hi - key_lo + 1, 1));
+      }
+    }
     for (int attempt = 0;; ++attempt) {
       wdb_agg_t *t = nullptr;
       if (wdb_agg_create(0, expect, needs, &t)) raise_core();
       std::unique_ptr<wdb_agg_t, int (*)(wdb_agg_t *)> guard(t, wdb_agg_destroy);
+      if (have_range && wdb_agg_set_key_range(t, 1, key_lo, key_hi)) raise_core();
       if (wdb_agg_consume(t, nullptr, dcols.data(), nc, val.c_str(), key.c_str(), cond.c_str(), n, 0)) raise_core();
       if (wdb_agg_size(t, nullptr, &groups)) {
         const std::string msg = wdb_last_error();

@@ -3,6 +3,7 @@
 #pragma once
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "arrow_utils.hpp"
@@ -57,5 +58,6 @@ private:
   bool owns_device_ = true;
   bool zone_pruning_ = true;
   std::map<std::string, void *> zonemaps_;
+  std::map<std::string, std::pair<long long, long long>> key_ranges_;   // min/max of integer GROUP BY columns
   long long last_zones_live_ = -1, last_zones_total_ = -1;
 };

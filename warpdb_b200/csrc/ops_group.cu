@@ -5,6 +5,7 @@
 // sums) and the std::map<int,AggData> loop of src/warpdb.cpp:373-437 (fp64 sum/count/min/max, key
 // ascending); jit_sort_pairs on the group arrays (src/warpdb.cpp:370-371) is the ordered export.
 #include <algorithm>
+#include <cctype>
 #include <cstring>
 
 #include "core.hpp"
@@ -21,6 +22,8 @@ struct wdb_agg {
   int64_t cap = 0;          // power of two
   char *mem = nullptr;
   wdb_table T{};
+  bool have_range = false;  // optimizer statistics: every key of the next consume calls lies in [key_lo, key_hi]
+  int64_t key_lo = 0, key_hi = -1;
 };
 
 using namespace wdb;
@@ -117,10 +120,11 @@ static unsigned grid_for(Device *d, long long n) {
   return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)d->num_sms * 16));
 }
 
-struct GroupPlan { GenSpec spec; int block, unroll, vec, smem_slots, wp_slots; size_t smem_bytes; const char *entry; };
+struct GroupPlan { GenSpec spec; int block, unroll, vec, smem_slots, wp_ids; size_t smem_bytes; const char *entry; };
+struct KeyRange { bool known; int64_t lo, hi; };
 
 static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const char *key, const char *cond, int needs,
-                      int64_t cap_hint, bool check_alignment, GroupPlan *p) {
+                      int64_t cap_hint, KeyRange range, bool check_alignment, GroupPlan *p) {
   const bool has_cond = cond && *cond;
   GenSpec &spec = p->spec;
   spec.kind = "group";
@@ -131,18 +135,17 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   p->unroll = (int)opt("group.unroll", 1);
   p->vec = (int)opt("group.vec", 4);
   if (p->vec != 4 && p->vec != 8) return fail("group.vec must be 4 or 8");
-  // Small cardinalities (and SUM/COUNT/AVG): warp-private tables without shared-memory atomics.
-  // Otherwise shared pre-aggregation with atomics pays while the distinct keys fit the CTA's table;
-  // beyond that every row misses it and the probes are wasted work.
-  const int64_t expected = cap_hint / 2;                     // cap_hint = table capacity = 2 x expected groups
-  int64_t wp = opt("group.wp_slots", -1);
+  // Small cardinalities with a known key range (SUM/COUNT/AVG): warp-private, directly indexed
+  // accumulators without shared-memory atomics (wdb_group_wp).  Otherwise shared pre-aggregation
+  // with atomics pays while the distinct keys fit the CTA's table; beyond that every row misses it
+  // and the probes are wasted work.
+  const int64_t span = range.known ? range.hi - range.lo + 1 : -1;
+  int64_t expected = cap_hint / 2;                           // cap_hint = table capacity = 2 x expected groups
+  if (span > 0) expected = std::min(expected, span);          // an integer key cannot form more groups than its range holds
+  const int64_t kMaxDyn = 232448 - 64;                       // sm_100: 227 KB per CTA
   const bool wp_ok = (needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0;
-  if (wp < 0) {   // auto: warp-private tables while a table of 2 x expected slots leaves room for >= 7 warps per SM
-    wp = 0;
-    if (expected <= 1024) { wp = 1024; while (wp < 2 * expected) wp <<= 1; }
-  }
-  if (!wp_ok) wp = 0;
-  if (wp & (wp - 1)) return fail("group.wp_slots must be a power of two");
+  int64_t wp = 0;
+  if (wp_ok && span > 0 && span <= opt("group.wp_max_span", 4096)) wp = (span + 7) / 8 * 8;
   int64_t slots = opt("group.smem_slots", -1);
   if (slots < 0) {
     slots = 0;
@@ -152,25 +155,23 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   int wp_ilp = 1;
   if (wp > 0) {
     slots = 0;
-    const size_t per_slot = 16 + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0);
-    int warps = (int)std::min<int64_t>(opt("group.wp_warps", 16), (int64_t)(232448 / (per_slot * wp)));
-    if (warps < 1) return fail("group.wp_slots too large for shared memory");
+    const int64_t per_id = 8 + 4 + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0);
+    int warps = (int)std::min<int64_t>(opt("group.wp_warps", 16), kMaxDyn / (per_id * wp));
+    if (warps < 1) return fail("key span too large for shared memory");
     p->block = 32 * warps;
     p->unroll = (int)opt("group.wp_unroll", 2);
     p->vec = (int)opt("group.wp_vec", 8);
-    wp_ilp = (int)opt("group.wp_ilp", 2);
+    wp_ilp = (int)opt("group.wp_ilp", 1);
     if (wp_ilp != 1 && wp_ilp != 2 && wp_ilp != 4) return fail("group.wp_ilp must be 1, 2 or 4");
-    p->smem_bytes = per_slot * (size_t)wp * warps;
+    p->smem_bytes = (size_t)(per_id * wp * warps);
     p->entry = "wdb_group_wp";
   } else {
     p->entry = "wdb_group";
   }
-  p->wp_slots = (int)wp;
+  p->wp_ids = (int)wp;
   p->smem_slots = (int)slots;
   int log2 = 0;
   while ((1ll << log2) < slots) ++log2;
-  int wplog2 = 0;
-  while ((1ll << wplog2) < wp) ++wplog2;
   if (wp == 0) {
     size_t per_slot = 8 + 4 + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0) + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) + ((needs & WDB_NEED_FIRST_BIT) ? 8 : 0);
     p->smem_bytes = per_slot * (size_t)slots;
@@ -179,7 +180,7 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   spec.defines = {{"WDB_VEC", p->vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("group.ld_hint", 0)}, {"WDB_ST_HINT", 0},
                   {"WDB_BLOCK", p->block}, {"WDB_UNROLL", p->unroll}, {"WDB_NEEDS", needs}, {"WDB_SMEM_SLOTS", slots},
                   {"WDB_SMEM_LOG2", log2}, {"WDB_SMEM_PROBES", opt("group.smem_probes", 4)}, {"WDB_HAS_COND", has_cond ? 1 : 0},
-                  {"WDB_WP_SLOTS", wp}, {"WDB_WP_LOG2", wplog2}, {"WDB_WP_PROBES", opt("group.wp_probes", 16)}, {"WDB_WP_ILP", wp_ilp}};
+                  {"WDB_WP_IDS", wp}, {"WDB_WP_ILP", wp_ilp}};
   spec.fns.push_back({"val", "float", (needs & ~WDB_NEED_CNT_BIT & ~WDB_NEED_FIRST_BIT) ? val : "0.0f"});  // COUNT never evaluates its argument (src/warpdb.cpp:376)
   spec.fns.push_back({"key", "int", key});
   if (has_cond) spec.fns.push_back({"cond", "bool", cond});
@@ -190,8 +191,34 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
 int gen_group_source(const wdb_col_t *cols, int ncols, const char *val, const char *key, const char *cond, int agg,
                      std::string *src) {
   GroupPlan p;
-  if (plan_group(cols, ncols, val, key, cond, needs_for_agg(agg), 2048, false, &p)) return 1;
+  const int64_t span = opt("group.debug_span", 0);   // introspection only: pretend the key range [0, span) is known
+  if (plan_group(cols, ncols, val, key, cond, needs_for_agg(agg), 2048, KeyRange{span > 0, 0, span - 1}, false, &p)) return 1;
   *src = gen_source(p.spec);
+  return 0;
+}
+
+// `key` names a single int32 column ("quantity[idx]", "(quantity[idx])" or "quantity"): its index in cols, else -1
+static int bare_int32_column(const char *key, const wdb_col_t *cols, int ncols) {
+  std::string k;
+  for (const char *p = key; *p; ++p)
+    if (!isspace((unsigned char)*p)) k.push_back(*p);
+  while (k.size() >= 2 && k.front() == '(' && k.back() == ')') k = k.substr(1, k.size() - 2);
+  const std::string suffix = "[idx]";
+  if (k.size() > suffix.size() && k.compare(k.size() - suffix.size(), suffix.size(), suffix) == 0) k.resize(k.size() - suffix.size());
+  for (int c = 0; c < ncols; ++c)
+    if (cols[c].name && k == cols[c].name && cols[c].dtype == WDB_INT32) return c;
+  return -1;
+}
+
+// Optimizer statistics gathered on demand: min/max of an integer GROUP BY column in one streaming
+// pass (4 B/row, ~0.6 ms per 1e9 rows) before the aggregation when the caller supplied none.  Not
+// cached: a (pointer, length) pair says nothing about the contents (allocators reuse addresses), and
+// a stale range sends every out-of-range row down the slow global path.
+static int auto_key_range(Device *d, cudaStream_t s, const wdb_col_t &col, int64_t n, KeyRange *out) {
+  const wdb_col_t c{col.name, col.dtype, col.dptr, n};
+  double lo = 0, hi = 0;
+  if (wdb_column_minmax(d->id, s, &c, &lo, &hi)) return 1;
+  *out = KeyRange{true, (int64_t)lo, (int64_t)hi};
   return 0;
 }
 
@@ -245,6 +272,15 @@ int wdb_agg_destroy(wdb_agg_t *t) {
   return 0;
 }
 
+int wdb_agg_set_key_range(wdb_agg_t *t, int known, int64_t lo, int64_t hi) {
+  if (!t) return fail("null table");
+  if (known && (lo > hi || lo < INT32_MIN || hi > INT32_MAX)) return fail("invalid key range [%lld, %lld]", (long long)lo, (long long)hi);
+  t->have_range = known != 0;
+  t->key_lo = lo;
+  t->key_hi = hi;
+  return 0;
+}
+
 int wdb_agg_reset(wdb_agg_t *t, void *stream) {
   if (!t) return fail("null table");
   WDB_CUDA(cudaSetDevice(t->dev->id));
@@ -262,8 +298,13 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   if (n < 0) return fail("negative row count");
   Device *d = t->dev;
   WDB_CUDA(cudaSetDevice(d->id));
+  KeyRange range{t->have_range, t->key_lo, t->key_hi};
+  if (!range.known && n >= opt("group.auto_stats_min_rows", 1 << 20) && (t->needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0) {
+    const int kc = bare_int32_column(key_expr, cols, ncols);
+    if (kc >= 0 && cols[kc].dptr && auto_key_range(d, (cudaStream_t)stream, cols[kc], n, &range)) return 1;
+  }
   GroupPlan p;
-  if (plan_group(cols, ncols, val_expr, key_expr, cond, t->needs, t->cap, true, &p)) return 1;
+  if (plan_group(cols, ncols, val_expr, key_expr, cond, t->needs, t->cap, range, true, &p)) return 1;
   Kernel k;
   if (get_kernel(d, gen_source(p.spec), "wdb_group.cu", p.entry, &k)) return 1;
   if (n == 0) return 0;
@@ -282,7 +323,7 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   // hash prefix is p, which occupy one contiguous 1/2^pass_bits of the table, so the random
   // read-modify-writes of a launch hit the L2 instead of DRAM.  Each launch re-reads the columns.
   unsigned pass_bits = 0;
-  if (p.wp_slots == 0 && p.smem_slots == 0) {
+  if (p.wp_ids == 0 && p.smem_slots == 0) {
     const double touched = (double)t->cap * (4.0 + ((t->needs & WDB_NEED_SUM_BIT) ? 8 : 0) + ((t->needs & WDB_NEED_CNT_BIT) ? 8 : 0) +
                                              ((t->needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) + ((t->needs & WDB_NEED_FIRST_BIT) ? 8 : 0));
     const double budget = (double)opt("group.l2_budget_mb", 48) * 1048576.0;
@@ -290,8 +331,9 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
     const int64_t forced = opt("group.pass_bits", -1);
     if (forced >= 0) pass_bits = (unsigned)forced;
   }
-  if (p.wp_slots > 0) {
-    void *args[] = {ptrs.data(), &nn, &rb, &t->T};
+  if (p.wp_ids > 0) {
+    int key_base = (int)range.lo;
+    void *args[] = {ptrs.data(), &nn, &rb, &t->T, &key_base};
     return launch(k, grid, p.block, p.smem_bytes, (cudaStream_t)stream, args);
   }
   for (unsigned pass = 0; pass < (1u << pass_bits); ++pass) {
@@ -338,6 +380,16 @@ int wdb_agg_size(wdb_agg_t *t, void *stream, int64_t *h_groups) {
   unsigned meta[4];
   if (read_meta(t, (cudaStream_t)stream, meta)) return 1;
   *h_groups = (int64_t)meta[0] + (meta[2] ? 1 : 0);
+  return 0;
+}
+
+int wdb_agg_spilled(wdb_agg_t *t, void *stream, int64_t *h_rows) {
+  if (!t || !h_rows) return fail("null argument");
+  WDB_CUDA(cudaSetDevice(t->dev->id));
+  unsigned meta[4];
+  WDB_CUDA(cudaMemcpyAsync(meta, t->T.meta, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  WDB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  *h_rows = meta[3];
   return 0;
 }
 

@@ -68,6 +68,16 @@ def synth_i32(n, seed, lo, hi_excl, row0=0, device=0):
     return out
 
 
+def column_minmax(column, name="col"):
+    """(min, max) of one device column in one streaming pass (wdb_column_minmax): the statistics the
+    reference's TableStats were meant to hold (include/csv_loader.hpp:22-37)."""
+    dev = column.device.index or 0
+    cols, _ = wc.make_cols(schema_of({name: column}))
+    lo, hi = C.c_double(0), C.c_double(0)
+    wc.check(wc.lib().wdb_column_minmax(dev, _stream(dev), cols, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
 class AggTable:
     """Device-resident hash aggregation table (wdb_agg_*): fold row chunks and partial aggregates of
     other GPUs into it, then export ordered groups."""
@@ -92,6 +102,11 @@ class AggTable:
     def reset(self):
         wc.check(wc.lib().wdb_agg_reset(self.handle, _stream(self.device)))
 
+    def set_key_range(self, lo=None, hi=None):
+        """Optimizer statistics: every key of the following consume calls lies in [lo, hi] (None: unknown)."""
+        known = lo is not None and hi is not None
+        wc.check(wc.lib().wdb_agg_set_key_range(self.handle, int(known), int(lo) if known else 0, int(hi) if known else -1))
+
     def consume(self, table, val_expr, key_expr, cond=None, n=None, row_base=0):
         n = num_rows(table) if n is None else n
         cols, nc = wc.make_cols(schema_of(table))
@@ -106,6 +121,12 @@ class AggTable:
         m = part["keys"].numel()
         wc.check(wc.lib().wdb_agg_merge(self.handle, _stream(self.device), p("keys"), p("sums"), p("counts"), p("mins"),
                                         p("maxs"), p("first"), m))
+
+    def spilled(self):
+        """Rows since the last reset that bypassed the shared-memory accumulators (tuning statistic)."""
+        g = C.c_int64(0)
+        wc.check(wc.lib().wdb_agg_spilled(self.handle, _stream(self.device), C.byref(g)))
+        return g.value
 
     def size(self):
         g = C.c_int64(0)

@@ -57,14 +57,37 @@ class CudaBackend:
             tab.reset()
         return tab
 
+    def _key_stats(self, tab, table, key):
+        """Optimizer statistics for GROUP BY on a bare integer column: its min/max (one streaming pass,
+        cached per column like the zone maps) lets the core index its accumulators directly."""
+        import re
+        from . import ops
+        m = re.fullmatch(r"\(?\s*([A-Za-z_]\w*)\[idx\]\s*\)?", key.strip())
+        col = table.get(m.group(1)) if m else None
+        if col is None or col.dtype != torch.int32 or col.numel() == 0:
+            tab.set_key_range(None, None)
+            return
+        if not hasattr(self, "_stats"):
+            self._stats = {}
+        import weakref
+        hit = self._stats.get(id(col))   # keyed by the tensor object (not its address) and checked against in-place writes
+        if hit is None or hit[0]() is not col or hit[1] != col._version:
+            if len(self._stats) > 64:
+                self._stats.clear()
+            hit = self._stats[id(col)] = (weakref.ref(col), col._version) + ops.column_minmax(col, m.group(1))
+        lo, hi = hit[2], hit[3]
+        tab.set_key_range(int(lo), int(hi))
+
     def group_local(self, table, val, key, cond, needs, expected, agg, order):
         """Single-GPU GROUP BY: aggregate and export once."""
         tab = self._table("partial", expected, needs)
+        self._key_stats(tab, table, key)
         tab.consume(table, val, key, cond, row_base=0)
         return tab.export(agg, order, raw=True)
 
     def group_partials(self, table, val, key, cond, needs, expected, row_base):
         tab = self._table("partial", expected, needs)
+        self._key_stats(tab, table, key)
         tab.consume(table, val, key, cond, row_base=row_base)
         agg = wc.SUM if needs & wc.NEED_SUM else (wc.COUNT if needs & wc.NEED_COUNT else wc.MIN)
         part = tab.export(agg, wc.ORDER_KEY_ASC, raw=True)
