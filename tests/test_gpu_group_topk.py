@@ -134,6 +134,75 @@ def test_key_range_statistics_select_direct_indexing_and_stay_correct_when_wrong
         np.testing.assert_allclose(out["sums"].cpu().numpy(), ref["sums"], rtol=1e-12)
 
 
+def test_direct_addressed_table_for_wide_integer_ranges():
+    """Key ranges too wide for shared memory but known to the optimizer use a direct-addressed table
+    (no probe, ordered export without a sort).  Covers: WHERE, negative keys, a range starting at
+    INT_MIN, stale statistics (keys outside the promised range), chunks with different ranges (flush +
+    re-prepare), merging partials afterwards (flush into the hash table), DESC export, -0.0 values."""
+    wc.set_option("group.auto_stats_min_rows", 0)
+    try:
+        n = 600_011
+        rng = np.random.default_rng(11)
+        price = orc.synth_f32(n, 97, -5.0, 100.0)
+        for keys in (rng.integers(-40_000, 60_000, n), -2**31 + rng.integers(0, 70_000, n), 2**31 - 1 - rng.integers(0, 70_000, n)):
+            t = {"price": price, "quantity": np.ascontiguousarray(keys, dtype=np.int32)}
+            d = dev(t)
+            for agg, cond, order in ((wc.SUM, None, wc.ORDER_KEY_ASC), (wc.AVG, "price > 20", wc.ORDER_KEY_DESC), (wc.COUNT, "price > 95", wc.ORDER_KEY_ASC)):
+                ref = orc.group_agg("price", "quantity", cond, t, agg=agg, order=order)
+                k, v = ops.group_agg(d, "price[idx]", "quantity[idx]", cu(cond), agg=agg, order=order, expected_groups=100_000)
+                assert np.array_equal(k.cpu().numpy(), ref["keys"])
+                if agg == wc.COUNT:
+                    assert np.array_equal(bits(v.cpu().numpy()), bits(ref["vals"]))
+                else:
+                    np.testing.assert_allclose(v.cpu().numpy(), ref["vals"], rtol=SUM_RTOL, atol=0)
+        # stale statistics + chunks with different ranges + partial merge
+        keys = rng.integers(0, 100_000, n).astype(np.int32)
+        t = {"price": price, "quantity": keys}
+        d = dev(t)
+        ref = orc.group_agg("price", "quantity", None, t, agg=orc.AVG)
+        tab = ops.AggTable(0, 100_000, wc.NEED_SUM | wc.NEED_COUNT)
+        third = n // 3 // 8 * 8
+        tab.set_key_range(0, 49_999)                                  # wrong: keys reach 99 999
+        tab.consume({k: v[:third] for k, v in d.items()}, "price[idx]", "quantity[idx]")
+        tab.set_key_range(10_000, 99_999)                             # not covered by the live range: flush, new side table
+        tab.consume({k: v[third:2 * third] for k, v in d.items()}, "price[idx]", "quantity[idx]", row_base=third)
+        part = ops.AggTable(0, 100_000, wc.NEED_SUM | wc.NEED_COUNT)
+        part.consume({k: v[2 * third:] for k, v in d.items()}, "price[idx]", "quantity[idx]", row_base=2 * third)   # statistics gathered by the core
+        tab.merge(part.export(wc.AVG, wc.ORDER_KEY_ASC))              # partials land in the hash table: the side table is flushed first
+        part.close()
+        out = tab.export(wc.AVG, wc.ORDER_KEY_ASC)
+        tab.close()
+        assert np.array_equal(out["keys"].cpu().numpy(), ref["keys"])
+        assert np.array_equal(out["counts"].cpu().numpy(), ref["counts"])
+        np.testing.assert_allclose(out["sums"].cpu().numpy(), ref["sums"], rtol=1e-12)
+        # merging partials into a fresh table whose key range is known: direct-addressed merge
+        halves = []
+        for a, b in ((0, n // 2 // 8 * 8), (n // 2 // 8 * 8, n)):
+            ptab = ops.AggTable(0, 100_000, wc.NEED_SUM | wc.NEED_COUNT)
+            ptab.consume({k: v[a:b] for k, v in d.items()}, "price[idx]", "quantity[idx]", row_base=a)
+            halves.append(ptab.export(wc.AVG, wc.ORDER_KEY_ASC))
+            ptab.close()
+        final = ops.AggTable(0, 100_000, wc.NEED_SUM | wc.NEED_COUNT)
+        final.set_key_range(0, 99_999)
+        for h in halves:
+            final.merge(h)
+        out = final.export(wc.AVG, wc.ORDER_KEY_DESC)
+        final.close()
+        assert np.array_equal(out["keys"].cpu().numpy(), ref["keys"][::-1])
+        assert np.array_equal(out["counts"].cpu().numpy(), ref["counts"][::-1])
+        np.testing.assert_allclose(out["sums"].cpu().numpy(), ref["sums"][::-1], rtol=1e-12)
+        # a group whose values are all -0.0 must still exist (untouched slots are recognised by the -0.0 bit pattern)
+        t2 = {"price": np.array([-0.0, -0.0, 1.5, -0.0], np.float32), "quantity": np.array([7, 7, 90_000, 5], np.int32)}
+        tab = ops.AggTable(0, 100_000, wc.NEED_SUM)
+        tab.set_key_range(0, 90_000)
+        tab.consume(dev(t2), "price[idx]", "quantity[idx]")
+        out = tab.export(wc.SUM, wc.ORDER_KEY_ASC)
+        tab.close()
+        assert out["keys"].cpu().tolist() == [5, 7, 90_000] and out["vals"].cpu().tolist() == [0.0, 0.0, 1.5]
+    finally:
+        wc.set_option("group.auto_stats_min_rows", None)
+
+
 def test_table_overflow_is_reported_and_retried():
     n = 300_000
     t = {"price": orc.synth_f32(n, 41, 0.0, 1.0), "quantity": np.arange(n, dtype=np.int32)}

@@ -43,10 +43,29 @@ __device__ __forceinline__ void wdb_group_row(const wdb_table &T,
 #endif
                                               int key, float val, i64 row, const u32 pass_bits, const u32 pass) {
   const double dv = (double)val;
+#if WDB_DENSE
+  {  // direct-addressed table: one native RED per accumulator, no probe (keys outside the promised range fall through)
+    // a table larger than the L2 is filled in several launches, launch i folding only the index
+    // slice [pass_bits, pass) (the two parameters carry the slice bounds in this mode), so that the
+    // random read-modify-writes of a launch stay L2-resident; the launch whose slice starts at 0
+    // also handles the keys outside the range
+    const u32 di = (u32)key - (u32)T.dlo;
+    if (di < T.dspan) {
+      if (di >= pass_bits && di < pass) {
+        if (WDB_NEEDS & WDB_NEED_SUM_BIT) atomicAdd(&T.dsums[di], dv + 0.0);
+        if (WDB_NEEDS & WDB_NEED_CNT_BIT) atomicAdd(&T.dcnts[di], 1ull);
+      }
+      return;
+    }
+    if (pass_bits != 0u) return;
+  }
+  const u32 hsh = wdb_hash32(key);
+#else
   const u32 hsh = wdb_hash32(key);
   // multi-pass mode (large tables): this launch only folds the keys whose hash prefix is `pass`,
   // i.e. one contiguous, L2-sized region of the global table
   if (pass_bits && (hsh >> (32u - pass_bits)) != pass) return;
+#endif
 #if WDB_SMEM_SLOTS > 0
   if (key != WDB_KEY_EMPTY) {
     u32 h = hsh >> (32 - WDB_SMEM_LOG2);

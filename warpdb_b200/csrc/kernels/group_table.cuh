@@ -27,7 +27,16 @@ struct wdb_table {
   unsigned int mask;
   unsigned int shift;   // 32 - log2(capacity): the slot of a key is the TOP bits of its hash, so keys
                         // whose hashes share a prefix live in one contiguous region of the table
+  // direct-addressed side table for integer keys with a known range (optimizer statistics): key k
+  // lives at index k - dlo, no probe and no CAS.  dsums start as -0.0 (WDB_DENSE_EMPTY): adding any
+  // value other than -0.0 changes the bit pattern, so an untouched slot is recognisable without a
+  // second atomic; -0.0 addends are added as +0.0.  dspan == 0: not in use.
+  double *dsums;
+  unsigned long long *dcnts;
+  int dlo;
+  unsigned int dspan;
 };
+#define WDB_DENSE_EMPTY 0x8000000000000000ull
 
 // monotone map double -> signed 64-bit (a < b  <=>  enc(a) < enc(b) for non-NaN values)
 __device__ __forceinline__ long long wdb_f64_enc(double d) {

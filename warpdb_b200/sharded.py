@@ -100,9 +100,16 @@ class CudaBackend:
             tab = self._tables[("partial", expected, needs)]
             return tab.export(agg, order, raw=True)
         tab = self._table("merge", expected, needs)
-        for p in parts:
-            if p["keys"].numel():
-                tab.merge(p)
+        live = [p for p in parts if p["keys"].numel()]
+        if sum(p["keys"].numel() for p in live) >= 1 << 20 and (needs & ~(wc.NEED_SUM | wc.NEED_COUNT)) == 0:
+            # partials are exported in key order: their first and last keys bound the range, which lets
+            # the core merge into a direct-addressed table (no probing, ordered export without a sort)
+            ends = torch.stack([torch.stack((p["keys"][0], p["keys"][-1])) for p in live]).cpu()
+            tab.set_key_range(int(ends[:, 0].min()), int(ends[:, 1].max()))
+        else:
+            tab.set_key_range(None, None)
+        for p in live:
+            tab.merge(p)
         return tab.export(agg, order, raw=True)
 
     def topk_local(self, table, key, val, cond, descending, k):
