@@ -60,7 +60,10 @@ class OracleBackend:
         order = np.argsort(-keys if descending else keys, kind="stable")[:k]
         return torch.from_numpy(vals[order]), torch.from_numpy(keys[order])
 
-    def topk_merge(self, vals, keys, descending, k, offset):
+    def topk_merge(self, vals, keys, descending, k, offset, valid=None):
+        if valid is not None:
+            keep = valid.numpy() > 0.5
+            vals, keys = vals[torch.from_numpy(keep)], keys[torch.from_numpy(keep)]
         kk = keys.numpy()
         order = np.argsort(-kk if descending else kk, kind="stable")[offset:offset + k]
         return vals[torch.from_numpy(order)]

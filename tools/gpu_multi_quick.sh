@@ -1,0 +1,16 @@
+#!/bin/bash
+# N-GPU check of the merge-bearing operators: NCCL parity tests + bench lines (N = visible GPUs)
+mkdir -p gpurun_out
+N=$(nvidia-smi -L | wc -l); echo "GPUs: $N"
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/pytest_multi$N.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_multi$N.log; tail -3 gpurun_out/pytest_multi$N.log
+for w in topk5 group1k group10m; do
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --workload $w --steps 20 --warmup 3 > gpurun_out/bench${N}_$w.json 2> gpurun_out/bench${N}_$w.err; echo "bench$N $w rc=$?"
+done
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob('gpurun_out/bench[248]_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split('/')[-1], 'n', d['n_gpus'], round(d['ms_per_step'],3),'ms', round(d['value']/1e9,1),'Grows/s', d['config'].get('result_checked'))
+    except Exception as e: print(f, 'ERR', e)
+PY

@@ -10,9 +10,10 @@ over devices with host-mediated copies and no inter-GPU traffic at all) for resi
     the reference's row order); compacted output needs only the exclusive scan of the per-rank
     survivor counts (an all_gather of one int64 per rank);
   * GROUP BY: every rank aggregates its shard into a partial table (keys + fp64 sums / counts /
-    minima / maxima); partials are hash-partitioned by key, exchanged with all_to_all, merged by
-    their owner and the final groups all_gathered ("exchange"), or -- for small tables -- simply
-    all_gathered and merged everywhere ("allgather");
+    minima / maxima) exported in key order; partials are range-partitioned by key (contiguous
+    slices, no permutation), exchanged with all_to_all, merged by their owner and the final groups
+    all_gathered -- already in key order ("exchange"), or -- for small tables -- simply all_gathered
+    and merged everywhere ("allgather");
   * ORDER BY ... LIMIT k: every rank selects its k+offset best (key, value) pairs, the candidates
     are all_gathered and the same selection runs once more on them; ties keep global row order
     because shards are ascending row ranges and candidates are concatenated in rank order.
@@ -116,11 +117,14 @@ class CudaBackend:
         from . import ops
         return ops.topk(table, key, val, cond, descending, k, 0, want_keys=True)
 
-    def topk_merge(self, vals, keys, descending, k, offset):
+    def topk_merge(self, vals, keys, descending, k, offset, valid=None):
         from . import ops
         if vals.numel() == 0:
             return vals
-        return ops.topk({"k": keys.contiguous(), "v": vals.contiguous()}, "k[idx]", "v[idx]", None, descending, k, offset)
+        if valid is None:
+            return ops.topk({"k": keys.contiguous(), "v": vals.contiguous()}, "k[idx]", "v[idx]", None, descending, k, offset)
+        return ops.topk({"k": keys.contiguous(), "v": vals.contiguous(), "ok": valid.contiguous()}, "k[idx]", "v[idx]", "(ok[idx] > 0.5f)",
+                        descending, k, offset)
 
 
 class ShardedDB:
@@ -156,18 +160,33 @@ class ShardedDB:
         dist.all_gather(bufs, pad, group=self.group)
         return [b[:s] for b, s in zip(bufs, sizes)]
 
-    def _all_to_all_var(self, pieces):
-        """pieces[r] goes to rank r; returns the list of tensors received (one per source rank)."""
+    def _all_gather_var_multi(self, tensors):
+        """all_gather of several 1-D tensors that share one (rank-dependent) length: ONE exchange of the
+        lengths and ONE collective for the data (the tensors travel packed in a byte buffer).
+        Returns, per tensor, the list of per-rank pieces."""
         if self.world == 1:
-            return [pieces[0]]
-        send_n = torch.tensor([p.numel() for p in pieces], dtype=torch.int64, device=self.device)
-        recv_n = torch.empty_like(send_n)
-        dist.all_to_all_single(recv_n, send_n, group=self.group)
-        recv_sizes = [int(x) for x in recv_n.tolist()]
-        send = torch.cat(pieces) if sum(p.numel() for p in pieces) else torch.empty(0, dtype=pieces[0].dtype, device=self.device)
-        recv = torch.empty(sum(recv_sizes), dtype=pieces[0].dtype, device=self.device)
-        dist.all_to_all_single(recv, send, output_split_sizes=recv_sizes, input_split_sizes=[p.numel() for p in pieces], group=self.group)
-        return list(torch.split(recv, recv_sizes))
+            return [[t] for t in tensors]
+        n = tensors[0].numel()
+        sizes_t = torch.tensor([n], dtype=torch.int64, device=self.device)
+        sizes = [torch.zeros_like(sizes_t) for _ in range(self.world)]
+        dist.all_gather(sizes, sizes_t, group=self.group)
+        sizes = torch.cat(sizes).tolist()
+        m = (max(max(sizes), 1) + 1) // 2 * 2                      # even: every packed segment stays 8-byte aligned
+        order = sorted(range(len(tensors)), key=lambda i: -tensors[i].element_size())
+        seg = [m * tensors[i].element_size() for i in order]
+        pack = torch.zeros(sum(seg), dtype=torch.uint8, device=self.device)
+        off = 0
+        for i, nb in zip(order, seg):
+            pack[off:off + n * tensors[i].element_size()] = tensors[i].contiguous().view(torch.uint8)
+            off += nb
+        bufs = [torch.empty_like(pack) for _ in range(self.world)]
+        dist.all_gather(bufs, pack, group=self.group)
+        out = [None] * len(tensors)
+        off = 0
+        for i, nb in zip(order, seg):
+            out[i] = [b[off:off + nb].view(tensors[i].dtype)[:sz] for b, sz in zip(bufs, sizes)]
+            off += nb
+        return out
 
     # ---- operators -----------------------------------------------------------------------------
     def query(self, expr, cond=None, mode=wc.DENSE_ZERO, gather=False):
@@ -205,26 +224,48 @@ class ShardedDB:
         if strategy == "auto":
             strategy = "allgather" if expected_groups <= 1 << 16 else "exchange"
         if strategy == "allgather":
-            gathered = {k: self._all_gather_var(part[k].contiguous()) for k in names}
+            pieces = self._all_gather_var_multi([part[k] for k in names])
+            gathered = dict(zip(names, pieces))
             parts = [{k: gathered[k][r] for k in names} for r in range(self.world)]
             return self.backend.merge_partials(parts, needs, expected_groups, agg, order)
-        # exchange: owner(key) = key mod world (non-negative); partials travel once to their owner
-        owner = torch.remainder(part["keys"].to(torch.int64), self.world)
-        perm = torch.argsort(owner, stable=True)
-        counts = torch.bincount(owner, minlength=self.world).tolist()
+        # exchange: range partitioning.  Partials are exported in key order, so the keys of owner r --
+        # the r-th equal slice of the global key range [lo, hi] -- are one contiguous piece of every
+        # rank's partial (no permutation), and the owners' final groups concatenated in rank order are
+        # already in key order (no final sort).  One tiny all_reduce finds lo and hi.
+        keys = part["keys"]
+        big = torch.iinfo(torch.int64).max
+        ends = torch.tensor([big, big], dtype=torch.int64, device=self.device)
+        if keys.numel():
+            ends = torch.stack((keys[0].to(torch.int64), -keys[-1].to(torch.int64)))
+        dist.all_reduce(ends, op=dist.ReduceOp.MIN, group=self.group)
+        lo, hi = int(ends[0]), -int(ends[1])
+        if lo == big:                                   # no rank has any group
+            return self.backend.merge_partials([part], needs, 1024, agg, order)
+        span = hi - lo + 1
+        bounds = torch.tensor([lo + (span * r + self.world - 1) // self.world for r in range(1, self.world)], dtype=keys.dtype, device=self.device)
+        cuts = [0] + torch.searchsorted(keys, bounds).tolist() + [keys.numel()]
+        counts = [cuts[r + 1] - cuts[r] for r in range(self.world)]
+        # the split sizes are the same for every column: exchange them once
+        send_n = torch.tensor(counts, dtype=torch.int64, device=self.device)
+        recv_n = torch.empty_like(send_n)
+        dist.all_to_all_single(recv_n, send_n, group=self.group)
+        recv_sizes = recv_n.tolist()
         recv = {}
         for k in names:
-            pieces = list(torch.split(part[k][perm].contiguous(), counts))
-            recv[k] = self._all_to_all_var(pieces)
+            send = part[k].contiguous()
+            buf = torch.empty(sum(recv_sizes), dtype=send.dtype, device=self.device)
+            dist.all_to_all_single(buf, send, output_split_sizes=recv_sizes, input_split_sizes=counts, group=self.group)
+            recv[k] = list(torch.split(buf, recv_sizes))
         parts = [{k: recv[k][r] for k in names} for r in range(self.world)]
-        mine = self.backend.merge_partials(parts, needs, max(expected_groups // self.world, 1024), agg, wc.ORDER_KEY_ASC)
-        # final groups of every owner, then one ordered view everywhere
+        mine = self.backend.merge_partials(parts, needs, max(2 * expected_groups // self.world, 1024), agg, wc.ORDER_KEY_ASC)
+        # final groups of every owner; rank order == key order
         final_names = [k for k in ("keys", "vals", "sums", "counts", "mins", "maxs", "first") if k in mine]
-        allg = {k: torch.cat(self._all_gather_var(mine[k].contiguous())) for k in final_names}
-        if order == wc.ORDER_FIRST:
-            idx = torch.argsort(allg["first"], stable=True)
-        else:
-            idx = torch.argsort(allg["keys"], stable=True, descending=(order == wc.ORDER_KEY_DESC))
+        allg = {k: torch.cat(p) for k, p in zip(final_names, self._all_gather_var_multi([mine[k] for k in final_names]))}
+        if order == wc.ORDER_KEY_ASC:
+            return allg
+        if order == wc.ORDER_KEY_DESC:
+            return {k: torch.flip(v, (0,)) for k, v in allg.items()}
+        idx = torch.argsort(allg["first"], stable=True)
         return {k: v[idx] for k, v in allg.items()}
 
     def topk(self, key, val=None, cond=None, descending=True, k=5, offset=0):
@@ -234,6 +275,19 @@ class ShardedDB:
         vals, keys = self.backend.topk_local(self.table, key, val or key, cond, descending, k + offset)
         if self.world == 1:
             return vals[offset:offset + k]
-        allv = torch.cat(self._all_gather_var(vals.contiguous()))
-        allk = torch.cat(self._all_gather_var(keys.contiguous()))
-        return self.backend.topk_merge(allv, allk, descending, k, offset)
+        m = k + offset
+        if m > 1 << 16:   # large limits: variable-length exchange (padding every rank to k + offset would dominate)
+            allv, allk = (torch.cat(x) for x in self._all_gather_var_multi([vals, keys]))
+            return self.backend.topk_merge(allv, allk, descending, k, offset)
+        # ONE fixed-size collective and no host synchronisation: [count | keys | vals] padded to k + offset
+        # candidates per rank; the padding is masked out by a validity column in the final selection
+        c = vals.numel()
+        pack = torch.zeros(2 * m + 1, dtype=torch.float32, device=self.device)
+        pack[0] = float(c)
+        pack[1:1 + c] = keys
+        pack[1 + m:1 + m + c] = vals
+        bufs = [torch.empty_like(pack) for _ in range(self.world)]
+        dist.all_gather(bufs, pack, group=self.group)
+        allp = torch.stack(bufs)
+        valid = (torch.arange(m, device=self.device, dtype=torch.float32)[None, :] < allp[:, :1]).to(torch.float32)
+        return self.backend.topk_merge(allp[:, 1 + m:].reshape(-1), allp[:, 1:1 + m].reshape(-1), descending, k, offset, valid=valid.reshape(-1))
