@@ -554,7 +554,20 @@ wdb_scatter(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
 #define WDB_SLAB_M 4
 #endif
 #define WDB_SLAB_CHUNKS (WDB_NWARPS * WDB_SLAB_M)
+// L2 residency hints (256-bit loads only): phase 1 parks the slab (evict_last), phase 2 releases it
+// (evict_first), the output streams past it (evict_first policy): 7-12 % (ncu showed only ~10 % of
+// the phase-2 sectors hitting the L2 without them).  Bulk-prefetching the NEXT slab into the L2
+// (cp.async.bulk.prefetch.L2, so that phase 1 reads L2 too) was tried and is 2x slower at every
+// slab size and prefetch granularity: two slabs per CTA no longer fit next to the output stream.
+#if WDB_L2_HINTS && WDB_VEC == 8 && WDB_ALIGNED
+#define WDB_L2_PARK 3
+#define WDB_L2_DROP 2
+#else
+#define WDB_L2_PARK WDB_LD_HINT
+#define WDB_L2_DROP WDB_LD_HINT
+#endif
 
+template <int H>
 __device__ __forceinline__ u32 wdb_chunk_flags(const wdb_cols &C, const i64 n, const i64 chunk, const u32 lane, const float wdb_tau,
                                                u32 (&flags)[WDB_UNROLL], float (&vals)[WDB_UNROLL][WDB_VEC],
 #if WDB_NOUT == 2
@@ -566,7 +579,7 @@ __device__ __forceinline__ u32 wdb_chunk_flags(const wdb_cols &C, const i64 n, c
   if ((chunk + 1) * WDB_WARP_ROWS <= n) {
     wdb_rows R[WDB_UNROLL];
 #pragma unroll
-    for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows(C, row0 + (i64)u * WDB_SLAB_ROWS, R[u]);
+    for (int u = 0; u < WDB_UNROLL; ++u) wdb_load_rows_h<H>(C, row0 + (i64)u * WDB_SLAB_ROWS, R[u]);
 #pragma unroll
     for (int u = 0; u < WDB_UNROLL; ++u) {
       u32 m = 0;
@@ -645,9 +658,9 @@ wdb_compact_l2(const wdb_cols C, float *__restrict__ out, float *__restrict__ ou
       u32 c = 0;
       if (chunk0 + m < nchunks) {
 #if WDB_NOUT == 2
-        c = wdb_chunk_flags(C, n, chunk0 + m, lane, wdb_tau, flags, vals, vals2, false);
+        c = wdb_chunk_flags<WDB_L2_PARK>(C, n, chunk0 + m, lane, wdb_tau, flags, vals, vals2, false);
 #else
-        c = wdb_chunk_flags(C, n, chunk0 + m, lane, wdb_tau, flags, vals, false);
+        c = wdb_chunk_flags<WDB_L2_PARK>(C, n, chunk0 + m, lane, wdb_tau, flags, vals, false);
 #endif
       }
 #pragma unroll
@@ -685,9 +698,9 @@ wdb_compact_l2(const wdb_cols C, float *__restrict__ out, float *__restrict__ ou
     for (int m = 0; m < WDB_SLAB_M; ++m) {
       if (chunk0 + m >= nchunks || ccount[m] == 0u) continue;   // warp-uniform
 #if WDB_NOUT == 2
-      wdb_chunk_flags(C, n, chunk0 + m, lane, wdb_tau, flags, vals, vals2, true);
+      wdb_chunk_flags<WDB_L2_DROP>(C, n, chunk0 + m, lane, wdb_tau, flags, vals, vals2, true);
 #else
-      wdb_chunk_flags(C, n, chunk0 + m, lane, wdb_tau, flags, vals, true);
+      wdb_chunk_flags<WDB_L2_DROP>(C, n, chunk0 + m, lane, wdb_tau, flags, vals, true);
 #endif
       u32 total = 0;
 #pragma unroll
@@ -715,9 +728,16 @@ wdb_compact_l2(const wdb_cols C, float *__restrict__ out, float *__restrict__ ou
       const int mis = (int)(g0 & 31);
       for (int i = (int)lane - mis; i < (int)total; i += 32)
         if (i >= 0 && g0 + i < out_cap) {
+#if WDB_L2_HINTS
+          wdb_st_f32_stream(out + g0 + i, s_stage[warp][i]);
+#if WDB_NOUT == 2
+          wdb_st_f32_stream(out2 + g0 + i, s_stage2[warp][i]);
+#endif
+#else
           out[g0 + i] = s_stage[warp][i];
 #if WDB_NOUT == 2
           out2[g0 + i] = s_stage2[warp][i];
+#endif
 #endif
         }
       __syncwarp();

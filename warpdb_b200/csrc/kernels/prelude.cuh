@@ -38,15 +38,29 @@ __device__ __forceinline__ void wdb_ldg16(const void *p, u32 (&r)[4]) {
 #endif
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
 }
-__device__ __forceinline__ void wdb_ldg32(const void *p, u32 (&r)[8]) {
-#if WDB_LD_HINT == 2
-  asm("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-#elif WDB_LD_HINT == 1
-  asm("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-#else
-  asm("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-#endif
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+// H: 0 plain | 1 L2::256B prefetch | 2 L2::evict_first (stream: do not displace what should stay)
+//    | 3 L2::evict_last (park: this line will be read again soon).  The L2 eviction qualifiers exist
+//    only for the 256-bit forms on sm_100.
+template <int H> __device__ __forceinline__ void wdb_ldg32h(const void *p, u32 (&r)[8]) {
+  if constexpr (H == 2)
+    asm("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+  else if constexpr (H == 3)
+    asm("ld.global.nc.L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+  else if constexpr (H == 1)
+    asm("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+  else
+    asm("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+__device__ __forceinline__ void wdb_ldg32(const void *p, u32 (&r)[8]) { wdb_ldg32h<WDB_LD_HINT>(p, r); }
+// scalar store with an L2 evict-first policy (output streams that must not displace parked input)
+__device__ __forceinline__ void wdb_st_f32_stream(float *p, float v) {
+  u64 pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(p), "f"(v), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void wdb_stg16(void *p, const u32 (&r)[4]) {
 #if WDB_ST_HINT == 1
@@ -79,12 +93,12 @@ template <class T> __device__ __forceinline__ T wdb_from_bits64(u32 lo, u32 hi) 
 
 // Load WDB_VEC consecutive rows of one column starting at row index `row` (a multiple of WDB_VEC
 // on the aligned path).
-template <class T> __device__ __forceinline__ void wdb_load_vec(const T *__restrict__ p, i64 row, T (&o)[WDB_VEC]) {
+template <int H, class T> __device__ __forceinline__ void wdb_load_vec_h(const T *__restrict__ p, i64 row, T (&o)[WDB_VEC]) {
 #if WDB_ALIGNED
   if constexpr (sizeof(T) == 4) {
 #if WDB_VEC == 8
     u32 r[8];
-    wdb_ldg32(p + row, r);
+    wdb_ldg32h<H>(p + row, r);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = wdb_from_bits32<T>(r[j]);
 #else
@@ -96,8 +110,8 @@ template <class T> __device__ __forceinline__ void wdb_load_vec(const T *__restr
   } else {
 #if WDB_VEC == 8
     u32 a[8], b[8];
-    wdb_ldg32(p + row, a);
-    wdb_ldg32(p + row + 4, b);
+    wdb_ldg32h<H>(p + row, a);
+    wdb_ldg32h<H>(p + row + 4, b);
 #pragma unroll
     for (int j = 0; j < 4; ++j) { o[j] = wdb_from_bits64<T>(a[2 * j], a[2 * j + 1]); o[4 + j] = wdb_from_bits64<T>(b[2 * j], b[2 * j + 1]); }
 #else
@@ -113,6 +127,7 @@ template <class T> __device__ __forceinline__ void wdb_load_vec(const T *__restr
   for (int j = 0; j < WDB_VEC; ++j) o[j] = __ldg(p + row + j);
 #endif
 }
+template <class T> __device__ __forceinline__ void wdb_load_vec(const T *__restrict__ p, i64 row, T (&o)[WDB_VEC]) { wdb_load_vec_h<WDB_LD_HINT>(p, row, o); }
 // coherent (read-write data) vector load of WDB_VEC floats: used to blend into the output buffer
 __device__ __forceinline__ void wdb_load_out_vec(const float *p, i64 row, float (&o)[WDB_VEC]) {
 #if WDB_ALIGNED && WDB_VEC == 8
