@@ -356,7 +356,16 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
       if (WDB_WP_HAS_CNT) cnt += all_cnts[w * WDB_WP_IDS + id];
     }
     if (!touched) continue;
-    const i64 g = wdb_table_slot(T, (int)((u32)key_base + id));
+    const int key = (int)((u32)key_base + id);
+#if WDB_DENSE
+    const u32 di = (u32)key - (u32)T.dlo;     // the host made the direct-addressed side table cover [key_base, key_base + WDB_WP_IDS)
+    if (di < T.dspan) {
+      if (WDB_WP_HAS_SUM) atomicAdd(&T.dsums[di], sum + 0.0);
+      if (WDB_WP_HAS_CNT) atomicAdd(&T.dcnts[di], cnt);
+      continue;
+    }
+#endif
+    const i64 g = wdb_table_slot(T, key);
     if (g >= 0) wdb_table_add<WDB_NEEDS>(T, g, sum, cnt, 0, 0, 0);
   }
 }

@@ -253,7 +253,7 @@ struct GroupPlan { GenSpec spec; int block, unroll, vec, smem_slots, wp_ids; siz
 struct KeyRange { bool known; int64_t lo, hi; };
 
 static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const char *key, const char *cond, int needs,
-                      int64_t cap_hint, KeyRange range, bool dense, bool check_alignment, GroupPlan *p) {
+                      int64_t cap_hint, KeyRange range, bool dense, bool use_wp, bool check_alignment, GroupPlan *p) {
   const bool has_cond = cond && *cond;
   GenSpec &spec = p->spec;
   spec.kind = "group";
@@ -274,9 +274,9 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   const int64_t kMaxDyn = 232448 - 64;                       // sm_100: 227 KB per CTA
   const bool wp_ok = (needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0;
   int64_t wp = 0;
-  if (!dense && wp_ok && span > 0 && span <= opt("group.wp_max_span", 4096)) wp = (span + 7) / 8 * 8;
+  if (use_wp && wp_ok && span > 0) wp = (span + 7) / 8 * 8;
   int64_t slots = opt("group.smem_slots", -1);
-  if (dense) {   // in-range rows go straight to the direct-addressed table: one RED each, nothing to pre-aggregate
+  if (dense && !use_wp) {   // in-range rows go straight to the direct-addressed table: one RED each, nothing to pre-aggregate
     slots = 0;
     p->block = (int)opt("group.dense_block", 512);
     p->unroll = (int)opt("group.dense_unroll", 1);
@@ -329,7 +329,7 @@ int gen_group_source(const wdb_col_t *cols, int ncols, const char *val, const ch
                      std::string *src) {
   GroupPlan p;
   const int64_t span = opt("group.debug_span", 0);   // introspection only: pretend the key range [0, span) is known
-  if (plan_group(cols, ncols, val, key, cond, needs_for_agg(agg), 2048, KeyRange{span > 0, 0, span - 1}, span > opt("group.wp_max_span", 4096), false, &p)) return 1;
+  if (plan_group(cols, ncols, val, key, cond, needs_for_agg(agg), 2048, KeyRange{span > 0, 0, span - 1}, span > 0, span > 0 && span <= opt("group.wp_max_span", 4096), false, &p)) return 1;
   *src = gen_source(p.spec);
   return 0;
 }
@@ -513,10 +513,13 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   const bool want_wp = sumcnt && span > 0 && span <= opt("group.wp_max_span", 4096);
   // (between the two, contention on few L2 addresses makes the hash table with its bigger footprint the faster one: measured 120 vs 88 Grows/s at 10 K keys)
   const bool want_dense = sumcnt && !want_wp && span >= opt("group.dense_min_span", 32768) && span <= opt("group.dense_max_span", 1 << 26);
-  if (t->dense_live && want_wp && wdb::dense_flush(t, (cudaStream_t)stream)) return 1;   // that kernel folds into the hash table
-  if (want_dense && n > 0 && wdb::dense_prepare(t, (cudaStream_t)stream, range.lo, span)) return 1;
+  // the warp-private kernel folds its per-CTA totals into a (tiny) direct-addressed table as well: the
+  // result is then in key order without a sort.  A small side table is a bad target for row-by-row
+  // atomics though (few L2 lines take them all), so any other kernel folds it into the hash table first.
+  if (t->dense_live && !want_wp && !want_dense && (int64_t)t->T.dspan < opt("group.dense_min_span", 32768) && wdb::dense_flush(t, (cudaStream_t)stream)) return 1;
+  if ((want_dense || want_wp) && n > 0 && wdb::dense_prepare(t, (cudaStream_t)stream, range.lo, span)) return 1;
   GroupPlan p;
-  if (plan_group(cols, ncols, val_expr, key_expr, cond, t->needs, t->cap, range, t->dense_live, true, &p)) return 1;
+  if (plan_group(cols, ncols, val_expr, key_expr, cond, t->needs, t->cap, range, t->dense_live, want_wp && t->dense_live, true, &p)) return 1;
   Kernel k;
   if (get_kernel(d, gen_source(p.spec), "wdb_group.cu", p.entry, &k)) return 1;
   if (n == 0) return 0;
@@ -586,7 +589,7 @@ int wdb_agg_merge(wdb_agg_t *t, void *stream, const int32_t *d_keys, const doubl
   // this table (wdb_agg_set_key_range) open a side table for the partials as they would for rows
   if (!t->dense_live && t->have_range && (needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0) {
     const int64_t span = t->key_hi - t->key_lo + 1;
-    if (span >= opt("group.dense_min_span", 32768) && span <= opt("group.dense_max_span", 1 << 26) && wdb::dense_prepare(t, s, t->key_lo, span)) return 1;
+    if (span >= 1 && span <= opt("group.dense_max_span", 1 << 26) && wdb::dense_prepare(t, s, t->key_lo, span)) return 1;
   }
 #define WDB_MERGE_CASE(N) case N: agg_merge_kernel<N><<<g, 256, 0, s>>>(t->T, d_keys, d_sums, (const long long *)d_counts, d_mins, d_maxs, (const long long *)d_first, m); break;
   switch (needs) {

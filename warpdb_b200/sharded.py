@@ -102,7 +102,7 @@ class CudaBackend:
             return tab.export(agg, order, raw=True)
         tab = self._table("merge", expected, needs)
         live = [p for p in parts if p["keys"].numel()]
-        if sum(p["keys"].numel() for p in live) >= 1 << 20 and (needs & ~(wc.NEED_SUM | wc.NEED_COUNT)) == 0:
+        if live and (needs & ~(wc.NEED_SUM | wc.NEED_COUNT)) == 0:
             # partials are exported in key order: their first and last keys bound the range, which lets
             # the core merge into a direct-addressed table (no probing, ordered export without a sort)
             ends = torch.stack([torch.stack((p["keys"][0], p["keys"][-1])) for p in live]).cpu()
