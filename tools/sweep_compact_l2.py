@@ -26,6 +26,8 @@ for sel in (0.01, 0.5, 0.99):
     cfgs = [{"l2_hints": 0}, {"l2_hints": 1}, {"variant": 2}]
     cfgs += [{"l2_hints": h, "slab_m": m, "min_ctas": c} for h, m, c in itertools.product((0, 1), (2, 4, 8), (2, 3, 4)) if not (m == 4 and c == 4)]
     cfgs += [{"l2_hints": 1, "slab_m": m, "min_ctas": c, "unroll": 2} for m, c in itertools.product((2, 4, 8), (4, 6, 8))]
+    if os.environ.get("QUICK"):
+        cfgs = cfgs[:3]
     for cfg in cfgs:
         for k in KEYS:
             wc.set_option("compact." + k, None)
