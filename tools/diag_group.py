@@ -24,8 +24,8 @@ for G in ((1000, 10_000_000) if len(sys.argv) < 3 else tuple(int(float(x)) for x
         cfgs += [{"group.pass_bits": b, "group.vec": 8, "group.unroll": 1, "group.ld_hint": 2} for b in (2, 3, 4)]
         cfgs += [{"group.pass_bits": b, "group.block": 256} for b in (2, 3)]
     for cfg in cfgs:
-        for k, v in {"group.smem_slots": -1, "group.vec": 4, "group.unroll": 2, "group.block": 512, "group.wp_slots": -1, "group.wp_unroll": 4,
-                     "group.wp_vec": 8, "group.wp_warps": 8, "group.pass_bits": -1, "group.ld_hint": 0}.items():
+        for k, v in {"group.smem_slots": -1, "group.vec": 4, "group.unroll": 2, "group.block": 512, "group.pass_bits": -1, "group.ld_hint": 0,
+                     "group.wp_max_span": 0, "group.dense_max_span": 0}.items():   # this tool times the hash-table paths only
             wc.set_option(k, v)
         for k, v in cfg.items():
             wc.set_option(k, v)

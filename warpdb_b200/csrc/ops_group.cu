@@ -225,7 +225,7 @@ dense_emit_kernel(wdb_table T, const unsigned long long *__restrict__ tile_offse
     } else {
       const unsigned long long o = desc ? g - 1ull - pos : pos;
       if (o_keys) o_keys[o] = key;
-      if (o_vals) o_vals[o] = agg == WDB_SUM ? (float)sum : (agg == WDB_AVG ? (float)(sum / (double)cnt) : (float)(double)cnt);   // src/warpdb.cpp:429-435
+      if (o_vals) o_vals[o] = agg == WDB_SUM ? (float)sum : (agg == WDB_AVG ? (float)(sum / (double)((NEEDS & WDB_NEED_CNT_BIT) ? cnt : 1ull)) : (float)(double)cnt);   // src/warpdb.cpp:429-435
       if (o_sums) o_sums[o] = sum;
       if (o_counts) o_counts[o] = (long long)cnt;
     }
