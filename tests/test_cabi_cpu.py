@@ -67,9 +67,11 @@ def test_compact_kernels(tmp_path):
         sass = sass_for(3, "k3.cubin")
         assert "wdb_compact_l2" in sass and "VOTE" in sass and "POPC" in sass and "LDG.E.64.STRONG.GPU" in sass
         assert re.search(r"LDG\.E\.NA\.\w+\.256", sass)
+        assert "LDG.E.NA.ELL2.256" in sass and "LDG.E.NA.EFL2.256" in sass   # phase 1 parks the slab in the L2, phase 2 releases it
+        assert "SHFL.UP" in sass                                               # survivors ranked with a warp scan of per-lane counts
         # two streaming passes (count -> scan -> scatter): no atomics, no block barriers
         sass = sass_for(2, "k2.cubin")
-        assert "wdb_count" in sass and "wdb_scatter" in sass and "VOTE" in sass and "POPC" in sass
+        assert "wdb_count" in sass and "wdb_scatter" in sass and "SHFL.UP" in sass and "POPC" in sass
         assert "ATOMG" not in sass and "BAR.SYNC" not in sass
         # single pass, TMA bulk-copy ring (UBLKCP + mbarrier), status-word look-back
         sass = sass_for(1, "k1.cubin")
