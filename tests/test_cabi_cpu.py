@@ -83,6 +83,14 @@ def test_compact_kernels(tmp_path):
         wc.set_option("compact.variant", None)
 
 
+def test_keyrange_kernel_evaluates_the_key_expression(tmp_path):
+    """Optimizer statistics on demand: min/max of the GROUP BY key expression (kernels/keyrange.cuh)."""
+    src, cubin = wc.debug_compile("keyrange", SCHEMA, "(quantity[idx] / 3.0f)")
+    assert "wdb_fn_key" in src and "(int)((quantity[idx] / 3.0f))" in src.replace("  ", " ")
+    sass = sass_of(cubin, tmp_path, "kr.cubin")
+    assert "wdb_keyrange" in sass and "REDUX.MIN.S32" in sass and "REDG.E.MAX.S32" in sass and re.search(r"LDG\.E\.NA\.\w+\.256", sass)
+
+
 def test_bulk_variant_emits_tma_bulk_copies(tmp_path):
     wc.set_option("project.variant", 2)
     try:

@@ -104,6 +104,13 @@ def test_warp_private_accumulators_any_key_distribution(opts):
                     assert np.array_equal(bits(v.cpu().numpy()), bits(ref["vals"]))
                 else:
                     np.testing.assert_allclose(v.cpu().numpy(), ref["vals"], rtol=SUM_RTOL, atol=0)
+        # key EXPRESSIONS: the core learns their range by evaluating the expression itself (keyrange.cuh)
+        t = {"price": orc.synth_f32(n, 93, -10.0, 100.0), "quantity": orc.synth_i32(n, 94, -3000, 3000)}
+        for key_text in ("quantity / 7", "price / 2", "quantity * 0 + 5"):
+            ref = orc.group_agg("price", key_text, "price > 5", t, agg=orc.AVG)
+            k, v = ops.group_agg(dev(t), "price[idx]", cu(key_text), cu("price > 5"), agg=wc.AVG, expected_groups=2000)
+            assert np.array_equal(k.cpu().numpy(), ref["keys"]), key_text
+            np.testing.assert_allclose(v.cpu().numpy(), ref["vals"], rtol=SUM_RTOL, atol=0)
     finally:
         wc.set_option("group.auto_stats_min_rows", None)
         for k in opts:

@@ -75,6 +75,7 @@ extern const char *const k_src_project;
 extern const char *const k_src_compact;
 extern const char *const k_src_group_table;
 extern const char *const k_src_group;
+extern const char *const k_src_keyrange;
 extern const char *const k_src_topk;
 
 }  // namespace wdb

@@ -475,6 +475,7 @@ int run_project(Device *d, cudaStream_t stream, const wdb_col_t *cols, int ncols
 int gen_compact_source(const wdb_col_t *cols, int ncols, const char *expr, const char *expr2, const char *cond,
                        bool assume_aligned, std::string *src);
 int gen_group_source(const wdb_col_t *cols, int ncols, const char *val, const char *key, const char *cond, int agg, std::string *src);
+int gen_keyrange_source(const wdb_col_t *cols, int ncols, const char *key, std::string *src);
 int gen_topk_source(const wdb_col_t *cols, int ncols, const char *key, const char *val, const char *cond, int desc, std::string *src);
 int gen_kernel_source(const std::string &kind, const wdb_col_t *cols, int ncols, const char *a, const char *b,
                       const char *cond, int mode, std::string *src, std::string *name) {
@@ -489,6 +490,10 @@ int gen_kernel_source(const std::string &kind, const wdb_col_t *cols, int ncols,
   if (kind == "compact") {
     *name = "wdb_compact.cu";
     return gen_compact_source(cols, ncols, a, b, cond, true, src);
+  }
+  if (kind == "keyrange") {
+    *name = "wdb_keyrange.cu";
+    return gen_keyrange_source(cols, ncols, a, src);
   }
   if (kind == "group") {
     *name = "wdb_group.cu";
