@@ -162,7 +162,7 @@ def make_workload(name, rows, rank, world, local):
         expr, cond = "(price[idx] * 0.9f)", "(price[idx] > 20.0f)"
         _, cnt = ops.project_filter(table, expr, cond, wc.COMPACT, out=out)
         return dict(step=lambda: ops.project_filter(table, expr, cond, wc.COMPACT, out=out, sync_count=False),
-                    bytes_per_row=4.0 + 4.0 * cnt / rows, kernel="wdb_compact", table=table, expr=expr, cond=cond,
+                    bytes_per_row=4.0 + 4.0 * cnt / rows, kernel="wdb_compact_l2", table=table, expr=expr, cond=cond,
                     query="price * 0.9 WHERE price > 20", selectivity=cnt / rows,
                     check=lambda: bool(torch.equal(out[:cnt][:1 << 20], (price[price > 20.0][:1 << 20] * 0.9))))
     if name.startswith("group"):
@@ -342,7 +342,7 @@ def run_ours(args):
     traffic = None
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"].get(w["kernel"])
-        if t and args.workload in ("projection", "topk5", "group1k"):
+        if t and args.workload in ("projection", "topk5", "group1k", "filter50"):   # the captures were taken on these configurations
             traffic = t["dram_bytes_per_row"] * rows
     except Exception:  # noqa: BLE001
         pass

@@ -28,6 +28,8 @@ for sel in (0.01, 0.5, 0.99):
     cfgs += [{"l2_hints": 1, "slab_m": m, "min_ctas": c, "unroll": 2} for m, c in itertools.product((2, 4, 8), (4, 6, 8))]
     if os.environ.get("QUICK"):
         cfgs = cfgs[:3]
+    if os.environ.get("SMALLBLOCK"):
+        cfgs = [{}] + [{"block": b, "min_ctas": c, "slab_m": m, "ctas_per_sm": 16} for b, c, m in ((128, 8, 4), (128, 8, 8), (128, 6, 8), (192, 5, 4), (192, 5, 6), (384, 2, 4), (384, 2, 3), (320, 3, 4), (256, 4, 3), (256, 4, 5), (256, 4, 6))]
     for cfg in cfgs:
         for k in KEYS:
             wc.set_option("compact." + k, None)

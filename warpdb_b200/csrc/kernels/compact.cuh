@@ -568,6 +568,9 @@ wdb_scatter(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
 // the phase-2 sectors hitting the L2 without them).  Bulk-prefetching the NEXT slab into the L2
 // (cp.async.bulk.prefetch.L2, so that phase 1 reads L2 too) was tried and is 2x slower at every
 // slab size and prefetch granularity: two slabs per CTA no longer fit next to the output stream.
+// Also tried: leaving the staged survivors through one bulk shared->global copy per chunk
+// (cp.async.bulk, UBLKCP.G.S) instead of the LDS/STG loop: 8 % slower at 1 % and 50 % selectivity,
+// equal at 99 % (the wait for the previous chunk's copy and the proxy fence cost more than the loop).
 #if WDB_L2_HINTS && WDB_VEC == 8 && WDB_ALIGNED
 #define WDB_L2_PARK 3
 #define WDB_L2_DROP 2
