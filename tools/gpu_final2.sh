@@ -18,8 +18,10 @@ for w in ('projection','filter1','filter50','filter99','group1k','group10m','top
         print(w, round(d['ms_per_step'],3),'ms', round(d['value']/1e9,1),'Grows/s', round(d['roofline']['achieved']),'GB/s', round(d['roofline']['frac'],3), d['config'].get('result_checked'), d['gpu_launches'], d.get('e2e',{}).get('value'))
     except Exception as e: print(w, 'ERR', e)
 PY
+if [ -z "$SKIP_DIAG" ]; then
 timeout 600 python tools/diag_group_wp.py 1e9 > gpurun_out/diag_group_wp.jsonl 2> gpurun_out/diag_group_wp.err; echo "diag wp rc=$?"
 timeout 600 python tools/diag_group_dense.py 1e9 > gpurun_out/diag_group_dense.jsonl 2> gpurun_out/diag_group_dense.err; echo "diag dense rc=$?"
+fi
 python bench.py --steps 5 --warmup 3 --no-e2e --no-ref --no-cpu > gpurun_out/plain_bench.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 5 --warmup 3 --no-e2e --no-ref --no-cpu > gpurun_out/ncu_bench.log 2>&1
