@@ -141,6 +141,23 @@ def test_key_range_statistics_select_direct_indexing_and_stay_correct_when_wrong
         np.testing.assert_allclose(out["sums"].cpu().numpy(), ref["sums"], rtol=1e-12)
 
 
+@pytest.mark.parametrize("agg", [wc.SUM, wc.AVG, wc.MAX])
+def test_sparse_keys_in_the_big_shared_table_tier(agg):
+    """2 K - 4 K sparse keys (no usable range): one 16 K-slot shared-memory table per SM where the
+    accumulators fit (SUM), the global hash table otherwise -- same groups either way."""
+    n = 600_017
+    rng = np.random.default_rng(13)
+    pool = rng.integers(-2**31, 2**31, 3000, dtype=np.int64).astype(np.int32)
+    t = {"price": orc.synth_f32(n, 98, -10.0, 100.0), "quantity": pool[rng.integers(0, len(pool), n)]}
+    ref = orc.group_agg("price", "quantity", "price > 0", t, agg=agg)
+    k, v = ops.group_agg(dev(t), "price[idx]", "quantity[idx]", cu("price > 0"), agg=agg, expected_groups=3000)
+    assert np.array_equal(k.cpu().numpy(), ref["keys"])
+    if agg == wc.MAX:
+        assert np.array_equal(bits(v.cpu().numpy()), bits(ref["vals"]))
+    else:
+        np.testing.assert_allclose(v.cpu().numpy(), ref["vals"], rtol=SUM_RTOL, atol=0)
+
+
 def test_direct_addressed_table_for_wide_integer_ranges():
     """Key ranges too wide for shared memory but known to the optimizer use a direct-addressed table
     (no probe, ordered export without a sort).  Covers: WHERE, negative keys, a range starting at
