@@ -96,11 +96,11 @@ def test_warp_private_accumulators_any_key_distribution(opts):
         for keys in (pool[rng.integers(0, len(pool), n)], rng.integers(-1, 2, n), rng.integers(-1000, 1000, n),
                      -2**31 + rng.integers(0, 900, n), 2**31 - 1 - rng.integers(0, 1500, n)):
             t = {"price": orc.synth_f32(n, 91, -10.0, 100.0), "quantity": np.ascontiguousarray(keys, dtype=np.int32)}
-            for agg, cond in ((wc.SUM, None), (wc.AVG, "price > 20"), (wc.COUNT, "price > 95")):
+            for agg, cond in ((wc.SUM, None), (wc.AVG, "price > 20"), (wc.COUNT, "price > 95"), (wc.MIN, "price > 20"), (wc.MAX, None)):
                 ref = orc.group_agg("price", "quantity", cond, t, agg=agg)
                 k, v = ops.group_agg(dev(t), "price[idx]", "quantity[idx]", cu(cond), agg=agg, expected_groups=2000)
                 assert np.array_equal(k.cpu().numpy(), ref["keys"])
-                if agg == wc.COUNT:
+                if agg in (wc.COUNT, wc.MIN, wc.MAX):
                     assert np.array_equal(bits(v.cpu().numpy()), bits(ref["vals"]))
                 else:
                     np.testing.assert_allclose(v.cpu().numpy(), ref["vals"], rtol=SUM_RTOL, atol=0)

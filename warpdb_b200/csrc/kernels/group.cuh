@@ -166,7 +166,7 @@ wdb_group(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T, 
 //   group id of a key:   key - key_base; the optimizer knows the key column's min/max
 //                        (wdb_agg_set_key_range / wdb_column_minmax).  Keys outside the promised
 //                        range stay correct: they are folded into the global table directly.
-//   accumulators:        struct of arrays per warp -- f64 sums[WDB_WP_IDS], u32 tags[], u32 counts[]
+//   accumulators:        struct of arrays per warp -- f64 sums[WDB_WP_IDS], i64 mins[] / maxs[], u32 tags[], u32 counts[]
 //                        (an array of 16-byte structs would put every tag in one of 8 banks)
 //   step (WDB_WP_ILP rows per lane), repeated while any lane is pending:
 //     1. STS.32  every pending lane writes a unique tag (lane + 32*i) for its id
@@ -186,17 +186,26 @@ wdb_group(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T, 
 #define WDB_WP_WARPS (WDB_BLOCK / 32)
 #define WDB_WP_HAS_SUM ((WDB_NEEDS & WDB_NEED_SUM_BIT) != 0)
 #define WDB_WP_HAS_CNT ((WDB_NEEDS & WDB_NEED_CNT_BIT) != 0)
+#define WDB_WP_HAS_MM ((WDB_NEEDS & WDB_NEED_MINMAX_BIT) != 0)
 #define WDB_WP_NOID 0xffffffffu
 
 // All of the kernel's shared memory is addressed as offsets from this one symbol so that every
 // access stays an LDS/STS (pointers kept in a struct decay to generic LD/ST once the struct is
 // passed to a non-inlined function).
-// layout: sums f64[WARPS][IDS] | tags u32[WARPS][IDS] | counts u32[WARPS][IDS] (if needed)
+// layout (each array [WARPS][IDS], present only when the aggregation needs it):
+//   sums f64 | mins i64 | maxs i64 (order-preserving encodings of f64) | tags u32 | counts u32
 extern __shared__ __align__(16) unsigned char wdb_wp_smem[];
 struct wdb_wp_state {
-  u32 sums, tags, cnts;   // byte offsets of this warp's accumulator arrays
+  u32 sums, mins, maxs, tags, cnts;   // byte offsets of this warp's accumulator arrays
   int key_base;
 };
+#define WDB_WP_OFF_SUMS 0u
+#define WDB_WP_OFF_MINS (WDB_WP_OFF_SUMS + (WDB_WP_HAS_SUM ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
+#define WDB_WP_OFF_MAXS (WDB_WP_OFF_MINS + (WDB_WP_HAS_MM ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
+#define WDB_WP_OFF_TAGS (WDB_WP_OFF_MAXS + (WDB_WP_HAS_MM ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
+#define WDB_WP_OFF_CNTS (WDB_WP_OFF_TAGS + 4u * WDB_WP_IDS * WDB_WP_WARPS)
+#define WDB_WP_MIN(W, id) (*reinterpret_cast<i64 *>(wdb_wp_smem + (W).mins + 8u * (id)))
+#define WDB_WP_MAX(W, id) (*reinterpret_cast<i64 *>(wdb_wp_smem + (W).maxs + 8u * (id)))
 #define WDB_WP_SUM(W, id) (*reinterpret_cast<double *>(wdb_wp_smem + (W).sums + 8u * (id)))
 #define WDB_WP_TAG(W, id) (*reinterpret_cast<u32 *>(wdb_wp_smem + (W).tags + 4u * (id)))
 #define WDB_WP_CNT(W, id) (*reinterpret_cast<u32 *>(wdb_wp_smem + (W).cnts + 4u * (id)))
@@ -204,7 +213,8 @@ struct wdb_wp_state {
 __device__ __noinline__ void wdb_wp_global_row(const wdb_table &T, const int key, const float val, const i64 row) {
   atomicAdd(&T.meta[3], 1u);   // statistics: rows that bypassed the shared-memory accumulators (wdb_agg_spilled)
   const i64 g = wdb_table_slot(T, key);
-  if (g >= 0) wdb_table_add<WDB_NEEDS>(T, g, (double)val, 1ull, 0, 0, row);
+  const i64 e = wdb_f64_enc((double)val);
+  if (g >= 0) wdb_table_add<WDB_NEEDS>(T, g, (double)val, 1ull, e, e, row);
 }
 
 // one step: NI rows per lane
@@ -235,12 +245,14 @@ __device__ __forceinline__ void wdb_wp_step(const wdb_table &T, const wdb_wp_sta
     __syncwarp();
     u32 t[NI], c[NI];
     double a[NI];
+    i64 mn[NI], mx[NI];
 #pragma unroll
     for (int i = 0; i < NI; ++i)
-      if (pending[i]) {       // tag, sum and count are read together: the sum does not wait for the tag compare
+      if (pending[i]) {       // tag and accumulators are read together: they do not wait for the tag compare
         t[i] = WDB_WP_TAG(W, id[i]);
         if (WDB_WP_HAS_SUM) a[i] = WDB_WP_SUM(W, id[i]);
         if (WDB_WP_HAS_CNT) c[i] = WDB_WP_CNT(W, id[i]);
+        if (WDB_WP_HAS_MM) { mn[i] = WDB_WP_MIN(W, id[i]); mx[i] = WDB_WP_MAX(W, id[i]); }
       }
     any_pending = false;
 #pragma unroll
@@ -248,6 +260,11 @@ __device__ __forceinline__ void wdb_wp_step(const wdb_table &T, const wdb_wp_sta
       if (pending[i] && t[i] == lane + 32u * i) {
         if (WDB_WP_HAS_SUM) WDB_WP_SUM(W, id[i]) = a[i] + (double)val[i];
         if (WDB_WP_HAS_CNT) WDB_WP_CNT(W, id[i]) = c[i] + 1u;
+        if (WDB_WP_HAS_MM) {   // extrema settle quickly: the stores are rare
+          const i64 e = wdb_f64_enc((double)val[i]);
+          if (e < mn[i]) WDB_WP_MIN(W, id[i]) = e;
+          if (e > mx[i]) WDB_WP_MAX(W, id[i]) = e;
+        }
         pending[i] = false;
       }
       any_pending |= pending[i];
@@ -294,16 +311,21 @@ __device__ __forceinline__ void wdb_wp_load(const wdb_cols &C, wdb_rows (&R)[WDB
 extern "C" __global__ void __launch_bounds__(WDB_BLOCK, 1)
 wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T, const int key_base) {
   const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  double *all_sums = reinterpret_cast<double *>(wdb_wp_smem);
-  u32 *all_tags = reinterpret_cast<u32 *>(wdb_wp_smem + 8u * WDB_WP_IDS * WDB_WP_WARPS);
-  u32 *all_cnts = all_tags + WDB_WP_IDS * WDB_WP_WARPS;
+  double *all_sums = reinterpret_cast<double *>(wdb_wp_smem + WDB_WP_OFF_SUMS);
+  i64 *all_mins = reinterpret_cast<i64 *>(wdb_wp_smem + WDB_WP_OFF_MINS);
+  i64 *all_maxs = reinterpret_cast<i64 *>(wdb_wp_smem + WDB_WP_OFF_MAXS);
+  u32 *all_tags = reinterpret_cast<u32 *>(wdb_wp_smem + WDB_WP_OFF_TAGS);
+  u32 *all_cnts = reinterpret_cast<u32 *>(wdb_wp_smem + WDB_WP_OFF_CNTS);
   wdb_wp_state W;
-  W.sums = 8u * WDB_WP_IDS * warp;
-  W.tags = 8u * WDB_WP_IDS * WDB_WP_WARPS + 4u * WDB_WP_IDS * warp;
-  W.cnts = 12u * WDB_WP_IDS * WDB_WP_WARPS + 4u * WDB_WP_IDS * warp;
+  W.sums = WDB_WP_OFF_SUMS + 8u * WDB_WP_IDS * warp;
+  W.mins = WDB_WP_OFF_MINS + 8u * WDB_WP_IDS * warp;
+  W.maxs = WDB_WP_OFF_MAXS + 8u * WDB_WP_IDS * warp;
+  W.tags = WDB_WP_OFF_TAGS + 4u * WDB_WP_IDS * warp;
+  W.cnts = WDB_WP_OFF_CNTS + 4u * WDB_WP_IDS * warp;
   W.key_base = key_base;
   for (int s = threadIdx.x; s < WDB_WP_IDS * WDB_WP_WARPS; s += WDB_BLOCK) {
-    all_sums[s] = 0.0;
+    if (WDB_WP_HAS_SUM) all_sums[s] = 0.0;
+    if (WDB_WP_HAS_MM) { all_mins[s] = WDB_ENC_PLUS_INF; all_maxs[s] = WDB_ENC_MINUS_INF; }
     all_tags[s] = WDB_WP_NOID;
     if (WDB_WP_HAS_CNT) all_cnts[s] = 0u;
   }
@@ -347,26 +369,28 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
   for (u32 id = threadIdx.x; id < (u32)WDB_WP_IDS; id += WDB_BLOCK) {
     double sum = 0.0;
     u64 cnt = 0ull;
+    i64 mn = WDB_ENC_PLUS_INF, mx = WDB_ENC_MINUS_INF;
     bool touched = false;
 #pragma unroll 1
     for (int w = 0; w < WDB_WP_WARPS; ++w) {
       if (all_tags[w * WDB_WP_IDS + id] == WDB_WP_NOID) continue;
       touched = true;
-      sum += all_sums[w * WDB_WP_IDS + id];
+      if (WDB_WP_HAS_SUM) sum += all_sums[w * WDB_WP_IDS + id];
       if (WDB_WP_HAS_CNT) cnt += all_cnts[w * WDB_WP_IDS + id];
+      if (WDB_WP_HAS_MM) { mn = min(mn, all_mins[w * WDB_WP_IDS + id]); mx = max(mx, all_maxs[w * WDB_WP_IDS + id]); }
     }
     if (!touched) continue;
     const int key = (int)((u32)key_base + id);
 #if WDB_DENSE
     const u32 di = (u32)key - (u32)T.dlo;     // the host made the direct-addressed side table cover [key_base, key_base + WDB_WP_IDS)
-    if (di < T.dspan) {
+    if (di < T.dspan && !WDB_WP_HAS_MM) {   // the side table holds sums and counts only
       if (WDB_WP_HAS_SUM) atomicAdd(&T.dsums[di], sum + 0.0);
       if (WDB_WP_HAS_CNT) atomicAdd(&T.dcnts[di], cnt);
       continue;
     }
 #endif
     const i64 g = wdb_table_slot(T, key);
-    if (g >= 0) wdb_table_add<WDB_NEEDS>(T, g, sum, cnt, 0, 0, 0);
+    if (g >= 0) wdb_table_add<WDB_NEEDS>(T, g, sum, cnt, mn, mx, 0);
   }
 }
 #endif

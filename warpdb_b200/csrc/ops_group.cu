@@ -272,7 +272,7 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   int64_t expected = cap_hint / 2;                           // cap_hint = table capacity = 2 x expected groups
   if (span > 0) expected = std::min(expected, span);          // an integer key cannot form more groups than its range holds
   const int64_t kMaxDyn = 232448 - 64;                       // sm_100: 227 KB per CTA
-  const bool wp_ok = (needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0;
+  const bool wp_ok = (needs & WDB_NEED_FIRST_BIT) == 0;
   int64_t wp = 0;
   if (use_wp && wp_ok && span > 0) wp = (span + 7) / 8 * 8;
   int64_t slots = opt("group.smem_slots", -1);
@@ -296,7 +296,7 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   int wp_ilp = 1;
   if (wp > 0) {
     slots = 0;
-    const int64_t per_id = 8 + 4 + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0);
+    const int64_t per_id = 4 + ((needs & WDB_NEED_SUM_BIT) ? 8 : 0) + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0) + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0);
     int warps = (int)std::min<int64_t>(opt("group.wp_warps", 16), kMaxDyn / (per_id * wp));
     if (warps < 1) return fail("key span too large for shared memory");
     p->block = 32 * warps;
@@ -335,7 +335,8 @@ int gen_group_source(const wdb_col_t *cols, int ncols, const char *val, const ch
                      std::string *src) {
   GroupPlan p;
   const int64_t span = opt("group.debug_span", 0);   // introspection only: pretend the key range [0, span) is known
-  if (plan_group(cols, ncols, val, key, cond, needs_for_agg(agg), 2048, KeyRange{span > 0, 0, span - 1}, span > 0, span > 0 && span <= opt("group.wp_max_span", 4096), false, &p)) return 1;
+  if (plan_group(cols, ncols, val, key, cond, needs_for_agg(agg), 2048, KeyRange{span > 0, 0, span - 1}, span > 0 && (needs_for_agg(agg) & WDB_NEED_MINMAX_BIT) == 0,
+                 span > 0 && span <= opt("group.wp_max_span", 4096), false, &p)) return 1;
   *src = gen_source(p.spec);
   return 0;
 }
@@ -535,7 +536,7 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   Device *d = t->dev;
   WDB_CUDA(cudaSetDevice(d->id));
   KeyRange range{t->have_range, t->key_lo, t->key_hi};
-  if (!range.known && n >= opt("group.auto_stats_min_rows", 1 << 20) && (t->needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0 &&
+  if (!range.known && n >= opt("group.auto_stats_min_rows", 1 << 20) && (t->needs & WDB_NEED_FIRST_BIT) == 0 &&
       auto_key_range(d, (cudaStream_t)stream, cols, ncols, key_expr, n, &range))
     return 1;
   // Integer keys with a known range: <= wp_max_span -> warp-private shared-memory accumulators;
@@ -543,16 +544,18 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   // a sort); otherwise the hash table.
   const bool sumcnt = (t->needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0;
   const int64_t span = range.known ? range.hi - range.lo + 1 : -1;
-  const bool want_wp = sumcnt && span > 0 && span <= opt("group.wp_max_span", 4096);
+  const bool want_wp = (t->needs & WDB_NEED_FIRST_BIT) == 0 && span > 0 && span <= opt("group.wp_max_span", 4096);
   // (between the two, contention on few L2 addresses makes the hash table with its bigger footprint the faster one: measured 120 vs 88 Grows/s at 10 K keys)
   const bool want_dense = sumcnt && !want_wp && span >= opt("group.dense_min_span", 32768) && span <= opt("group.dense_max_span", 1 << 26);
-  // the warp-private kernel folds its per-CTA totals into a (tiny) direct-addressed table as well: the
-  // result is then in key order without a sort.  A small side table is a bad target for row-by-row
-  // atomics though (few L2 lines take them all), so any other kernel folds it into the hash table first.
-  if (t->dense_live && !want_wp && !want_dense && (int64_t)t->T.dspan < opt("group.dense_min_span", 32768) && wdb::dense_flush(t, (cudaStream_t)stream)) return 1;
-  if ((want_dense || want_wp) && n > 0 && wdb::dense_prepare(t, (cudaStream_t)stream, range.lo, span)) return 1;
+  // the warp-private kernel folds its per-CTA totals into a (tiny) direct-addressed table as well (SUM /
+  // COUNT / AVG; extrema go to the hash table): the result is then in key order without a sort.  A small
+  // side table is a bad target for row-by-row atomics though (few L2 lines take them all), so any other
+  // kernel folds it into the hash table first.
+  const bool wp_side = want_wp && sumcnt;
+  if (t->dense_live && !wp_side && !want_dense && (int64_t)t->T.dspan < opt("group.dense_min_span", 32768) && wdb::dense_flush(t, (cudaStream_t)stream)) return 1;
+  if ((want_dense || wp_side) && n > 0 && wdb::dense_prepare(t, (cudaStream_t)stream, range.lo, span)) return 1;
   GroupPlan p;
-  if (plan_group(cols, ncols, val_expr, key_expr, cond, t->needs, t->cap, range, t->dense_live, want_wp && t->dense_live, true, &p)) return 1;
+  if (plan_group(cols, ncols, val_expr, key_expr, cond, t->needs, t->cap, range, t->dense_live, want_wp && (t->dense_live || !sumcnt), true, &p)) return 1;
   Kernel k;
   if (get_kernel(d, gen_source(p.spec), "wdb_group.cu", p.entry, &k)) return 1;
   if (n == 0) return 0;
