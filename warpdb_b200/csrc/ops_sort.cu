@@ -5,9 +5,17 @@
 // equal keys keep their original order in both directions; descending order is obtained by
 // complementing the key, which keeps the LSD passes stable.
 //
-// Three kernels per digit pass: per-chunk digit histogram -> exclusive scan of the
-// (digit-major) chunk histograms -> stable scatter with warp-ballot ranking.  Memory bound:
-// 2 reads + 1 write of the keys (and payloads) per pass.
+// Three kernels per digit pass (memory traffic: 2 reads + 1 write of the keys and payloads):
+//   sort_hist_kernel     every CTA owns a contiguous chunk of tiles and counts its digits
+//   sort_scan_kernel     exclusive scan of the digit-major (digit, CTA) counters -> global offsets
+//   sort_scatter_kernel  the CTA walks its chunk tile by tile (4 096 keys): every warp ranks its 512
+//                        keys digit by digit with ballots (stable: rounds and lanes in memory order,
+//                        a warp-private digit counter carried from round to round, no atomics), the
+//                        tile is permuted into digit order in shared memory and copied out so that
+//                        equal digits leave as contiguous runs (coalesced writes instead of one
+//                        32-byte sector per 4-byte key).
+// Measured on a B200, 2^28 float keys: see DESIGN.md section 3.5 (the first version of this file -- one
+// key per thread per round, scattered stores, a single-block scan over 16 M counters -- took 132 ms).
 #include <algorithm>
 
 #include "core.hpp"
@@ -16,19 +24,24 @@ namespace wdb {
 
 constexpr int kSortBlock = 256;
 constexpr int kSortWarps = kSortBlock / 32;
+constexpr int kSortTileBytes = 16384;                 // keys of one tile in shared memory
 
 template <class K> __device__ __forceinline__ unsigned digit_of(K key, int shift) { return (unsigned)(key >> shift) & 255u; }
+template <class K> struct SortTile { static constexpr int kItems = kSortTileBytes / (int)sizeof(K) / kSortBlock; static constexpr int kTile = kItems * kSortBlock; };
 
 template <class K>
 __global__ void __launch_bounds__(kSortBlock) sort_hist_kernel(const K *__restrict__ keys, long long n, long long chunk, int shift,
-                                                               unsigned *__restrict__ hist /* [256][nchunks] */, long long nchunks) {
-  __shared__ unsigned s_hist[256];
-  s_hist[threadIdx.x] = 0;
+                                                               unsigned *__restrict__ hist /* [256][nctas] */, long long nctas) {
+  __shared__ unsigned s_hist[kSortWarps][256];       // warp-private histograms: native 32-bit shared atomics, no inter-warp contention
+  for (int w = 0; w < kSortWarps; ++w) s_hist[w][threadIdx.x] = 0;
   __syncthreads();
+  const unsigned warp = threadIdx.x >> 5;
   const long long begin = (long long)blockIdx.x * chunk, end = min(begin + chunk, n);
-  for (long long i = begin + threadIdx.x; i < end; i += kSortBlock) atomicAdd(&s_hist[digit_of(keys[i], shift)], 1u);
+  for (long long i = begin + threadIdx.x; i < end; i += kSortBlock) atomicAdd(&s_hist[warp][digit_of(keys[i], shift)], 1u);
   __syncthreads();
-  hist[(long long)threadIdx.x * nchunks + blockIdx.x] = s_hist[threadIdx.x];
+  unsigned t = 0;
+  for (int w = 0; w < kSortWarps; ++w) t += s_hist[w][threadIdx.x];
+  hist[(long long)threadIdx.x * nctas + blockIdx.x] = t;
 }
 
 // exclusive scan of `m` counters into 64-bit offsets, one block
@@ -53,45 +66,90 @@ template <class K, bool HAS_PAYLOAD>
 __global__ void __launch_bounds__(kSortBlock) sort_scatter_kernel(const K *__restrict__ keys_in, K *__restrict__ keys_out,
                                                                   const unsigned *__restrict__ pay_in, unsigned *__restrict__ pay_out,
                                                                   long long n, long long chunk, int shift,
-                                                                  const long long *__restrict__ offs, long long nchunks) {
-  __shared__ long long s_base[256];                 // running output offset per digit for this chunk
-  __shared__ unsigned s_wcount[kSortWarps][256];    // per-warp digit counts of the current round
+                                                                  const long long *__restrict__ offs, long long nctas) {
+  constexpr int ITEMS = SortTile<K>::kItems, TILE = SortTile<K>::kTile;
+  __shared__ K s_keys[TILE];
+  __shared__ unsigned s_pay[HAS_PAYLOAD ? TILE : 1];
+  __shared__ unsigned s_wcnt[kSortWarps][256];      // per-warp digit counts of the tile, then exclusive prefixes over warps
+  __shared__ unsigned s_dstart[256];                // first position of a digit in the tile's digit order
+  __shared__ long long s_gbase[256];                // running global offset of a digit for this CTA
+  __shared__ long long s_gpos[256];                 // global position of tile-order index i with digit d: s_gpos[d] + i
+  __shared__ unsigned s_wtot[kSortWarps];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  s_base[threadIdx.x] = offs[(long long)threadIdx.x * nchunks + blockIdx.x];
+  const unsigned lt = (1u << lane) - 1u;
+  s_gbase[threadIdx.x] = offs[(long long)threadIdx.x * nctas + blockIdx.x];
   const long long begin = (long long)blockIdx.x * chunk, end = min(begin + chunk, n);
-  for (long long r0 = begin; r0 < end; r0 += kSortBlock) {
-    for (int w = 0; w < kSortWarps; ++w) s_wcount[w][threadIdx.x] = 0;
+  for (long long t0 = begin; t0 < end; t0 += TILE) {
+    const int count = (int)min((long long)TILE, end - t0);
+    for (int w = 0; w < kSortWarps; ++w) s_wcnt[w][threadIdx.x] = 0;
     __syncthreads();
-    const long long i = r0 + threadIdx.x;
-    const bool valid = i < end;
-    K key = 0;
-    unsigned pay = 0;
-    if (valid) { key = keys_in[i]; if (HAS_PAYLOAD) pay = pay_in[i]; }
-    const unsigned d = digit_of(key, shift);
-    // lanes of this warp holding the same digit (8 ballots); invalid lanes form their own class
-    unsigned peers = __ballot_sync(0xffffffffu, valid);
-    if (!valid) peers = ~peers;
+    // warp-striped load: item r of lane l is element warp*32*ITEMS + r*32 + l of the tile (memory order = (warp, r, lane))
+    K key[ITEMS];
+    unsigned pay[HAS_PAYLOAD ? ITEMS : 1], rank[ITEMS];
+    const int wbase = (int)warp * 32 * ITEMS;
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
-      peers &= ((d >> b) & 1u) ? bal : ~bal;
+    for (int r = 0; r < ITEMS; ++r) {
+      const int i = wbase + r * 32 + (int)lane;
+      key[r] = 0;
+      if (HAS_PAYLOAD) pay[r] = 0;
+      if (i < count) { key[r] = keys_in[t0 + i]; if (HAS_PAYLOAD) pay[r] = pay_in[t0 + i]; }
     }
-    const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-    if (valid && rank == 0) s_wcount[warp][d] = __popc(peers);
-    __syncthreads();
-    // digit `threadIdx.x`: turn per-warp counts into exclusive prefixes, advance the chunk offset
-    {
-      unsigned run = 0;
 #pragma unroll
-      for (int w = 0; w < kSortWarps; ++w) { const unsigned c = s_wcount[w][threadIdx.x]; s_wcount[w][threadIdx.x] = run; run += c; }
-      __syncthreads();
-      if (valid) {
-        const long long pos = s_base[d] + s_wcount[warp][d] + rank;
-        keys_out[pos] = key;
-        if (HAS_PAYLOAD) pay_out[pos] = pay;
+    for (int r = 0; r < ITEMS; ++r) {
+      const bool valid = wbase + r * 32 + (int)lane < count;
+      const unsigned d = digit_of(key[r], shift);
+      // lanes of this warp holding the same digit in this round (8 ballots); invalid lanes form their own class
+      unsigned peers = __ballot_sync(0xffffffffu, valid);
+      if (!valid) peers = ~peers;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+        peers &= ((d >> b) & 1u) ? bal : ~bal;
       }
-      __syncthreads();
-      s_base[threadIdx.x] += run;
+      const int leader = __ffs(peers) - 1;
+      unsigned old = 0;
+      if (valid && (int)lane == leader) { old = s_wcnt[warp][d]; s_wcnt[warp][d] = old + __popc(peers); }   // one writer per digit per round
+      old = __shfl_sync(0xffffffffu, old, leader);
+      rank[r] = old + __popc(peers & lt);
+      __syncwarp();
+    }
+    __syncthreads();
+    // digit `threadIdx.x`: exclusive prefix over the warps, tile total, then the digit's start in tile order
+    unsigned run = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) { const unsigned c = s_wcnt[w][threadIdx.x]; s_wcnt[w][threadIdx.x] = run; run += c; }
+    unsigned incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (unsigned)o) incl += y;
+    }
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    unsigned wpre = 0;
+    for (unsigned w = 0; w < warp; ++w) wpre += s_wtot[w];
+    const unsigned dstart = wpre + incl - run;
+    s_dstart[threadIdx.x] = dstart;
+    s_gpos[threadIdx.x] = s_gbase[threadIdx.x] - (long long)dstart;
+    s_gbase[threadIdx.x] += run;
+    __syncthreads();
+    // permute the tile into digit order (stable) in shared memory
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+      if (wbase + r * 32 + (int)lane < count) {
+        const unsigned d = digit_of(key[r], shift);
+        const unsigned pos = s_dstart[d] + s_wcnt[warp][d] + rank[r];
+        s_keys[pos] = key[r];
+        if (HAS_PAYLOAD) s_pay[pos] = pay[r];
+      }
+    }
+    __syncthreads();
+    // copy out: neighbours in tile order with the same digit are neighbours in the output
+    for (int i = threadIdx.x; i < count; i += kSortBlock) {
+      const K k = s_keys[i];
+      const long long pos = s_gpos[digit_of(k, shift)] + i;
+      keys_out[pos] = k;
+      if (HAS_PAYLOAD) pay_out[pos] = s_pay[i];
     }
     __syncthreads();
   }
@@ -146,8 +204,11 @@ static unsigned grid_for(Device *d, long long n) {
 template <class K>
 int radix_sort(Device *d, cudaStream_t s, K *keys, K *tmp_keys, unsigned *pay, unsigned *tmp_pay, long long n, int key_bits) {
   if (n <= 1) return 0;
-  long long chunk = 4096;
-  while ((n + chunk - 1) / chunk > 65536) chunk *= 2;
+  // every CTA owns a contiguous chunk of whole tiles; ~8 CTAs per SM keep the scan small (256 x nctas counters)
+  const long long tile = SortTile<K>::kTile;
+  const long long ntiles = (n + tile - 1) / tile;
+  const long long nctas = std::max<long long>(1, std::min<long long>(ntiles, (long long)d->num_sms * 8));
+  const long long chunk = (ntiles + nctas - 1) / nctas * tile;
   const long long nchunks = (n + chunk - 1) / chunk;
   const size_t hist_bytes = sizeof(unsigned) * 256 * (size_t)nchunks, offs_bytes = sizeof(long long) * 256 * (size_t)nchunks;
   void *hist = nullptr;
