@@ -104,6 +104,12 @@ def test_warp_private_accumulators_any_key_distribution(opts):
                     assert np.array_equal(bits(v.cpu().numpy()), bits(ref["vals"]))
                 else:
                     np.testing.assert_allclose(v.cpu().numpy(), ref["vals"], rtol=SUM_RTOL, atol=0)
+        # first-appearance order (jit_group_sum's contract, src/jit.cpp:196-213): smallest row id per key, kept per warp
+        t = {"price": orc.synth_f32(n, 91, -10.0, 100.0), "quantity": np.ascontiguousarray(rng.integers(-700, 700, n), dtype=np.int32)}
+        ref = orc.group_agg("price", "quantity", "price > 50", t, agg=orc.SUM, order=orc.ORDER_FIRST)
+        k, v = ops.group_agg(dev(t), "price[idx]", "quantity[idx]", cu("price > 50"), agg=wc.SUM, order=wc.ORDER_FIRST, expected_groups=2000)
+        assert np.array_equal(k.cpu().numpy(), ref["keys"])
+        np.testing.assert_allclose(v.cpu().numpy(), ref["vals"], rtol=SUM_RTOL, atol=0)
         # key EXPRESSIONS: the core learns their range by evaluating the expression itself (keyrange.cuh)
         t = {"price": orc.synth_f32(n, 93, -10.0, 100.0), "quantity": orc.synth_i32(n, 94, -3000, 3000)}
         for key_text in ("quantity / 7", "price / 2", "quantity * 0 + 5"):

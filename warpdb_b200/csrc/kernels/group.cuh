@@ -187,25 +187,28 @@ wdb_group(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table T, 
 #define WDB_WP_HAS_SUM ((WDB_NEEDS & WDB_NEED_SUM_BIT) != 0)
 #define WDB_WP_HAS_CNT ((WDB_NEEDS & WDB_NEED_CNT_BIT) != 0)
 #define WDB_WP_HAS_MM ((WDB_NEEDS & WDB_NEED_MINMAX_BIT) != 0)
+#define WDB_WP_HAS_FIRST ((WDB_NEEDS & WDB_NEED_FIRST_BIT) != 0)
 #define WDB_WP_NOID 0xffffffffu
 
 // All of the kernel's shared memory is addressed as offsets from this one symbol so that every
 // access stays an LDS/STS (pointers kept in a struct decay to generic LD/ST once the struct is
 // passed to a non-inlined function).
 // layout (each array [WARPS][IDS], present only when the aggregation needs it):
-//   sums f64 | mins i64 | maxs i64 (order-preserving encodings of f64) | tags u32 | counts u32
+//   sums f64 | mins i64 | maxs i64 (order-preserving encodings of f64) | first i64 (smallest row id) | tags u32 | counts u32
 extern __shared__ __align__(16) unsigned char wdb_wp_smem[];
 struct wdb_wp_state {
-  u32 sums, mins, maxs, tags, cnts;   // byte offsets of this warp's accumulator arrays
+  u32 sums, mins, maxs, first, tags, cnts;   // byte offsets of this warp's accumulator arrays
   int key_base;
 };
 #define WDB_WP_OFF_SUMS 0u
 #define WDB_WP_OFF_MINS (WDB_WP_OFF_SUMS + (WDB_WP_HAS_SUM ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
 #define WDB_WP_OFF_MAXS (WDB_WP_OFF_MINS + (WDB_WP_HAS_MM ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
-#define WDB_WP_OFF_TAGS (WDB_WP_OFF_MAXS + (WDB_WP_HAS_MM ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
+#define WDB_WP_OFF_FIRST (WDB_WP_OFF_MAXS + (WDB_WP_HAS_MM ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
+#define WDB_WP_OFF_TAGS (WDB_WP_OFF_FIRST + (WDB_WP_HAS_FIRST ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
 #define WDB_WP_OFF_CNTS (WDB_WP_OFF_TAGS + 4u * WDB_WP_IDS * WDB_WP_WARPS)
 #define WDB_WP_MIN(W, id) (*reinterpret_cast<i64 *>(wdb_wp_smem + (W).mins + 8u * (id)))
 #define WDB_WP_MAX(W, id) (*reinterpret_cast<i64 *>(wdb_wp_smem + (W).maxs + 8u * (id)))
+#define WDB_WP_FIRST(W, id) (*reinterpret_cast<i64 *>(wdb_wp_smem + (W).first + 8u * (id)))
 #define WDB_WP_SUM(W, id) (*reinterpret_cast<double *>(wdb_wp_smem + (W).sums + 8u * (id)))
 #define WDB_WP_TAG(W, id) (*reinterpret_cast<u32 *>(wdb_wp_smem + (W).tags + 4u * (id)))
 #define WDB_WP_CNT(W, id) (*reinterpret_cast<u32 *>(wdb_wp_smem + (W).cnts + 4u * (id)))
@@ -245,7 +248,7 @@ __device__ __forceinline__ void wdb_wp_step(const wdb_table &T, const wdb_wp_sta
     __syncwarp();
     u32 t[NI], c[NI];
     double a[NI];
-    i64 mn[NI], mx[NI];
+    i64 mn[NI], mx[NI], fr[NI];
 #pragma unroll
     for (int i = 0; i < NI; ++i)
       if (pending[i]) {       // tag and accumulators are read together: they do not wait for the tag compare
@@ -253,6 +256,7 @@ __device__ __forceinline__ void wdb_wp_step(const wdb_table &T, const wdb_wp_sta
         if (WDB_WP_HAS_SUM) a[i] = WDB_WP_SUM(W, id[i]);
         if (WDB_WP_HAS_CNT) c[i] = WDB_WP_CNT(W, id[i]);
         if (WDB_WP_HAS_MM) { mn[i] = WDB_WP_MIN(W, id[i]); mx[i] = WDB_WP_MAX(W, id[i]); }
+        if (WDB_WP_HAS_FIRST) fr[i] = WDB_WP_FIRST(W, id[i]);
       }
     any_pending = false;
 #pragma unroll
@@ -265,6 +269,7 @@ __device__ __forceinline__ void wdb_wp_step(const wdb_table &T, const wdb_wp_sta
           if (e < mn[i]) WDB_WP_MIN(W, id[i]) = e;
           if (e > mx[i]) WDB_WP_MAX(W, id[i]) = e;
         }
+        if (WDB_WP_HAS_FIRST && row0 + i < fr[i]) WDB_WP_FIRST(W, id[i]) = row0 + i;   // first appearance = smallest row id
         pending[i] = false;
       }
       any_pending |= pending[i];
@@ -314,18 +319,21 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
   double *all_sums = reinterpret_cast<double *>(wdb_wp_smem + WDB_WP_OFF_SUMS);
   i64 *all_mins = reinterpret_cast<i64 *>(wdb_wp_smem + WDB_WP_OFF_MINS);
   i64 *all_maxs = reinterpret_cast<i64 *>(wdb_wp_smem + WDB_WP_OFF_MAXS);
+  i64 *all_first = reinterpret_cast<i64 *>(wdb_wp_smem + WDB_WP_OFF_FIRST);
   u32 *all_tags = reinterpret_cast<u32 *>(wdb_wp_smem + WDB_WP_OFF_TAGS);
   u32 *all_cnts = reinterpret_cast<u32 *>(wdb_wp_smem + WDB_WP_OFF_CNTS);
   wdb_wp_state W;
   W.sums = WDB_WP_OFF_SUMS + 8u * WDB_WP_IDS * warp;
   W.mins = WDB_WP_OFF_MINS + 8u * WDB_WP_IDS * warp;
   W.maxs = WDB_WP_OFF_MAXS + 8u * WDB_WP_IDS * warp;
+  W.first = WDB_WP_OFF_FIRST + 8u * WDB_WP_IDS * warp;
   W.tags = WDB_WP_OFF_TAGS + 4u * WDB_WP_IDS * warp;
   W.cnts = WDB_WP_OFF_CNTS + 4u * WDB_WP_IDS * warp;
   W.key_base = key_base;
   for (int s = threadIdx.x; s < WDB_WP_IDS * WDB_WP_WARPS; s += WDB_BLOCK) {
     if (WDB_WP_HAS_SUM) all_sums[s] = 0.0;
     if (WDB_WP_HAS_MM) { all_mins[s] = WDB_ENC_PLUS_INF; all_maxs[s] = WDB_ENC_MINUS_INF; }
+    if (WDB_WP_HAS_FIRST) all_first[s] = 0x7fffffffffffffffll;
     all_tags[s] = WDB_WP_NOID;
     if (WDB_WP_HAS_CNT) all_cnts[s] = 0u;
   }
@@ -369,7 +377,7 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
   for (u32 id = threadIdx.x; id < (u32)WDB_WP_IDS; id += WDB_BLOCK) {
     double sum = 0.0;
     u64 cnt = 0ull;
-    i64 mn = WDB_ENC_PLUS_INF, mx = WDB_ENC_MINUS_INF;
+    i64 mn = WDB_ENC_PLUS_INF, mx = WDB_ENC_MINUS_INF, fr = 0x7fffffffffffffffll;
     bool touched = false;
 #pragma unroll 1
     for (int w = 0; w < WDB_WP_WARPS; ++w) {
@@ -378,19 +386,20 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
       if (WDB_WP_HAS_SUM) sum += all_sums[w * WDB_WP_IDS + id];
       if (WDB_WP_HAS_CNT) cnt += all_cnts[w * WDB_WP_IDS + id];
       if (WDB_WP_HAS_MM) { mn = min(mn, all_mins[w * WDB_WP_IDS + id]); mx = max(mx, all_maxs[w * WDB_WP_IDS + id]); }
+      if (WDB_WP_HAS_FIRST) fr = min(fr, all_first[w * WDB_WP_IDS + id]);
     }
     if (!touched) continue;
     const int key = (int)((u32)key_base + id);
 #if WDB_DENSE
     const u32 di = (u32)key - (u32)T.dlo;     // the host made the direct-addressed side table cover [key_base, key_base + WDB_WP_IDS)
-    if (di < T.dspan && !WDB_WP_HAS_MM) {   // the side table holds sums and counts only
+    if (di < T.dspan && !WDB_WP_HAS_MM && !WDB_WP_HAS_FIRST) {   // the side table holds sums and counts only
       if (WDB_WP_HAS_SUM) atomicAdd(&T.dsums[di], sum + 0.0);
       if (WDB_WP_HAS_CNT) atomicAdd(&T.dcnts[di], cnt);
       continue;
     }
 #endif
     const i64 g = wdb_table_slot(T, key);
-    if (g >= 0) wdb_table_add<WDB_NEEDS>(T, g, sum, cnt, mn, mx, 0);
+    if (g >= 0) wdb_table_add<WDB_NEEDS>(T, g, sum, cnt, mn, mx, fr);
   }
 }
 #endif

@@ -249,6 +249,17 @@ static unsigned grid_for(Device *d, long long n) {
   return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)d->num_sms * 16));
 }
 
+// warp-private accumulators (wdb_group_wp): bytes per key and whether at least 4 warps per SM fit
+static int64_t wp_bytes_per_id(int needs) {
+  return 4 + ((needs & WDB_NEED_SUM_BIT) ? 8 : 0) + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0) + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) +
+         ((needs & WDB_NEED_FIRST_BIT) ? 8 : 0);
+}
+constexpr int64_t kMaxDynSmem = 232448 - 64;   // sm_100: 227 KB per CTA
+static bool wp_fits(int needs, int64_t span) {
+  if (span <= 0 || span > opt("group.wp_max_span", 4096)) return false;
+  return kMaxDynSmem / (wp_bytes_per_id(needs) * ((span + 7) / 8 * 8)) >= 4;   // fewer warps cannot hide the shared-memory latency
+}
+
 struct GroupPlan { GenSpec spec; int block, unroll, vec, smem_slots, wp_ids; size_t smem_bytes; const char *entry; };
 struct KeyRange { bool known; int64_t lo, hi; };
 
@@ -271,10 +282,10 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   const int64_t span = range.known ? range.hi - range.lo + 1 : -1;
   int64_t expected = cap_hint / 2;                           // cap_hint = table capacity = 2 x expected groups
   if (span > 0) expected = std::min(expected, span);          // an integer key cannot form more groups than its range holds
-  const int64_t kMaxDyn = 232448 - 64;                       // sm_100: 227 KB per CTA
-  const bool wp_ok = (needs & WDB_NEED_FIRST_BIT) == 0;
+  const int64_t kMaxDyn = kMaxDynSmem;
   int64_t wp = 0;
-  if (use_wp && wp_ok && span > 0) wp = (span + 7) / 8 * 8;
+  const int64_t wp_per_id = wp_bytes_per_id(needs);
+  if (use_wp && wp_fits(needs, span)) wp = (span + 7) / 8 * 8;
   int64_t slots = opt("group.smem_slots", -1);
   if (dense && !use_wp) {   // in-range rows go straight to the direct-addressed table: one RED each, nothing to pre-aggregate
     slots = 0;
@@ -296,7 +307,7 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   int wp_ilp = 1;
   if (wp > 0) {
     slots = 0;
-    const int64_t per_id = 4 + ((needs & WDB_NEED_SUM_BIT) ? 8 : 0) + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0) + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0);
+    const int64_t per_id = wp_per_id;
     int warps = (int)std::min<int64_t>(opt("group.wp_warps", 16), kMaxDyn / (per_id * wp));
     if (warps < 1) return fail("key span too large for shared memory");
     p->block = 32 * warps;
@@ -335,8 +346,8 @@ int gen_group_source(const wdb_col_t *cols, int ncols, const char *val, const ch
                      std::string *src) {
   GroupPlan p;
   const int64_t span = opt("group.debug_span", 0);   // introspection only: pretend the key range [0, span) is known
-  if (plan_group(cols, ncols, val, key, cond, needs_for_agg(agg), 2048, KeyRange{span > 0, 0, span - 1}, span > 0 && (needs_for_agg(agg) & WDB_NEED_MINMAX_BIT) == 0,
-                 span > 0 && span <= opt("group.wp_max_span", 4096), false, &p)) return 1;
+  if (plan_group(cols, ncols, val, key, cond, needs_for_agg(agg), 2048, KeyRange{span > 0, 0, span - 1}, span > 0 && (needs_for_agg(agg) & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0,
+                 wp_fits(needs_for_agg(agg), span), false, &p)) return 1;
   *src = gen_source(p.spec);
   return 0;
 }
@@ -536,7 +547,7 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   Device *d = t->dev;
   WDB_CUDA(cudaSetDevice(d->id));
   KeyRange range{t->have_range, t->key_lo, t->key_hi};
-  if (!range.known && n >= opt("group.auto_stats_min_rows", 1 << 20) && (t->needs & WDB_NEED_FIRST_BIT) == 0 &&
+  if (!range.known && n >= opt("group.auto_stats_min_rows", 1 << 20) &&
       auto_key_range(d, (cudaStream_t)stream, cols, ncols, key_expr, n, &range))
     return 1;
   // Integer keys with a known range: <= wp_max_span -> warp-private shared-memory accumulators;
@@ -544,7 +555,7 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   // a sort); otherwise the hash table.
   const bool sumcnt = (t->needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0;
   const int64_t span = range.known ? range.hi - range.lo + 1 : -1;
-  const bool want_wp = (t->needs & WDB_NEED_FIRST_BIT) == 0 && span > 0 && span <= opt("group.wp_max_span", 4096);
+  const bool want_wp = wp_fits(t->needs, span);
   // (between the two, contention on few L2 addresses makes the hash table with its bigger footprint the faster one: measured 120 vs 88 Grows/s at 10 K keys)
   const bool want_dense = sumcnt && !want_wp && span >= opt("group.dense_min_span", 32768) && span <= opt("group.dense_max_span", 1 << 26);
   // the warp-private kernel folds its per-CTA totals into a (tiny) direct-addressed table as well (SUM /
