@@ -571,6 +571,11 @@ wdb_scatter(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
 // Also tried: leaving the staged survivors through one bulk shared->global copy per chunk
 // (cp.async.bulk, UBLKCP.G.S) instead of the LDS/STG loop: 8 % slower at 1 % and 50 % selectivity,
 // equal at 99 % (the wait for the previous chunk's copy and the proxy fence cost more than the loop).
+// And: staging the survivors already in phase 1 when a slab is sparse (so that phase 2, the second
+// read, is skipped): only 3 % faster at 1 % selectivity, 14 % at 0.1 %, 3 % slower at 50 % -- even
+// with phase 2 empty the kernel streams 4 GB in 0.84 ms (73 % of the copy peak): what bounds it at low
+// selectivity is the count phase itself (4 vector loads in flight per warp, a barrier and a
+// look-back per slab), not the re-read.
 #if WDB_L2_HINTS && WDB_VEC == 8 && WDB_ALIGNED
 #define WDB_L2_PARK 3
 #define WDB_L2_DROP 2
