@@ -673,6 +673,17 @@ wdb_compact_l2(const wdb_cols C, float *__restrict__ out, float *__restrict__ ou
 #pragma unroll
     for (int m = 0; m < WDB_SLAB_M; ++m) {
       u32 c = 0;
+#if WDB_PF_NEXT
+      // the warp's chunk m + WDB_PF_NEXT starts its way from HBM to the L2 now (no registers involved):
+      // its loads later see L2 latency, which multiplies the bytes a warp keeps in flight during the count phase
+#pragma unroll
+      for (int a = (m == 0 ? 1 : WDB_PF_NEXT); a <= WDB_PF_NEXT; ++a)
+        if (m + a < WDB_SLAB_M && (chunk0 + m + a + 1) * WDB_WARP_ROWS <= n) {
+          const i64 prow = (chunk0 + m + a) * WDB_WARP_ROWS + (i64)lane * WDB_VEC;
+#pragma unroll
+          for (int u = 0; u < WDB_UNROLL; ++u) wdb_prefetch_rows(C, prow + (i64)u * WDB_SLAB_ROWS);
+        }
+#endif
       if (chunk0 + m < nchunks) {
 #if WDB_NOUT == 2
         c = wdb_chunk_flags<WDB_L2_PARK>(C, n, chunk0 + m, lane, wdb_tau, flags, vals, vals2, false);

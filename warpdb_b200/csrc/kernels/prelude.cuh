@@ -62,6 +62,8 @@ __device__ __forceinline__ void wdb_st_f32_stream(float *p, float v) {
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(p), "f"(v), "l"(pol) : "memory");
 }
+// non-blocking prefetch of the line holding `p` into the L2 (no destination register)
+__device__ __forceinline__ void wdb_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(p)); }
 __device__ __forceinline__ void wdb_stg16(void *p, const u32 (&r)[4]) {
 #if WDB_ST_HINT == 1
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"

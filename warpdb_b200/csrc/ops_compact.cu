@@ -95,7 +95,7 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
                   {"WDB_ST_HINT", 0}, {"WDB_BLOCK", block}, {"WDB_UNROLL", unroll}, {"WDB_NOUT", two ? 2 : 1},
                   {"WDB_THRESH", two ? thresh : 0}, {"WDB_MIN_CTAS", opt("compact.min_ctas", variant == 3 ? 4 : 1)},
                   {"WDB_LB", opt("compact.lookback", variant == 1 ? 4 : 1)}, {"WDB_BULK", variant == 1 ? 1 : 0}, {"WDB_TWOPASS", variant == 2 ? 1 : 0}, {"WDB_PRUNE", prune ? 1 : 0},
-                  {"WDB_L2PASS", variant == 3 ? 1 : 0}, {"WDB_SLAB_M", opt("compact.slab_m", 4)}, {"WDB_L2_HINTS", opt("compact.l2_hints", 1)}};
+                  {"WDB_L2PASS", variant == 3 ? 1 : 0}, {"WDB_SLAB_M", opt("compact.slab_m", 4)}, {"WDB_L2_HINTS", opt("compact.l2_hints", 1)}, {"WDB_PF_NEXT", opt("compact.pf_next", 1)}};
   if (variant == 1) spec.defines.push_back({"WDB_TILE", p->tile_rows});
   spec.fns.push_back({"expr", "float", expr});
   if (two) spec.fns.push_back({"expr2", "float", expr2});

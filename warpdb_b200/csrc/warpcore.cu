@@ -177,6 +177,9 @@ std::string gen_source(const GenSpec &spec) {
   o << "__device__ __forceinline__ void wdb_load_rows(const wdb_cols &C, i64 row, wdb_rows &R) {";
   for (size_t k = 0; k < nu; ++k) o << " wdb_load_vec(C.c" << k << ", row, R.c" << k << ");";
   o << " }\n";
+  o << "__device__ __forceinline__ void wdb_prefetch_rows(const wdb_cols &C, i64 row) {";
+  for (size_t k = 0; k < nu; ++k) o << " wdb_prefetch_l2(C.c" << k << " + row);";
+  o << " }\n";
   o << "template <int H> __device__ __forceinline__ void wdb_load_rows_h(const wdb_cols &C, i64 row, wdb_rows &R) {";
   for (size_t k = 0; k < nu; ++k) o << " wdb_load_vec_h<H>(C.c" << k << ", row, R.c" << k << ");";
   o << " }\n";
