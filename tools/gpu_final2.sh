@@ -22,6 +22,7 @@ if [ -z "$SKIP_DIAG" ]; then
 timeout 600 python tools/diag_group_wp.py 1e9 > gpurun_out/diag_group_wp.jsonl 2> gpurun_out/diag_group_wp.err; echo "diag wp rc=$?"
 timeout 600 python tools/diag_group_dense.py 1e9 > gpurun_out/diag_group_dense.jsonl 2> gpurun_out/diag_group_dense.err; echo "diag dense rc=$?"
 fi
+timeout 300 python tools/diag_sort.py > gpurun_out/diag_sort.jsonl 2>&1; echo "diag sort rc=$?"; cat gpurun_out/diag_sort.jsonl
 python bench.py --steps 5 --warmup 3 --no-e2e --no-ref --no-cpu > gpurun_out/plain_bench.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 5 --warmup 3 --no-e2e --no-ref --no-cpu > gpurun_out/ncu_bench.log 2>&1
