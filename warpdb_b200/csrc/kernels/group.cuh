@@ -1,19 +1,26 @@
-// group.cuh -- fused filter + hash GROUP BY consume kernel (replaces the <<<1,1>>> linear-probe
+// group.cuh -- fused filter + GROUP BY consume kernels (replace the <<<1,1>>> linear-probe
 // `group_kernel` of src/jit.cpp:192-215 and the std::map loop of src/warpdb.cpp:373-385).
 //
 // key = (int)KEY(row) exactly as `int key = <expr>` (src/jit.cpp:200); accumulators are fp64
-// (src/warpdb.cpp:379-384).  Every CTA pre-aggregates into a private shared-memory hash table
-// (WDB_SMEM_SLOTS slots, native 32-bit CAS on the key, CAS-loop fp64 add -- sm_100 has no native
-// shared fp64 atomic) and folds it into the global open-addressing table once, at the end; rows
-// that do not find a shared slot within WDB_SMEM_PROBES probes go to the global table directly
-// (native RED.ADD.F64 in L2).  With WDB_SMEM_SLOTS == 0 every row goes straight to global memory
-// (large group counts).
+// (src/warpdb.cpp:379-384).  Two kernels, four accumulator layouts (the host picks one from the
+// key's min/max statistics, ops_group.cu):
+//   wdb_group     every CTA pre-aggregates into a private shared-memory hash table
+//                 (WDB_SMEM_SLOTS slots, native 32-bit CAS on the key, CAS-loop fp64 add -- sm_100 has
+//                 no native shared fp64 atomic) and folds it into the global open-addressing table
+//                 once, at the end; rows that do not find a shared slot within WDB_SMEM_PROBES probes
+//                 go to the global table directly (native RED.ADD.F64 in L2).  WDB_SMEM_SLOTS == 0:
+//                 every row goes straight to global memory (large group counts).  WDB_DENSE: keys
+//                 inside the known range go to a direct-addressed table instead (one RED, no probe).
+//   wdb_group_wp  narrow key ranges: warp-private, directly indexed accumulators in shared memory
+//                 updated with plain read-modify-writes (no shared-memory atomics); see below.
 //
-// Roofline: nominally HBM (8 B/row for price,quantity) but in practice bound by the shared-memory
-// atomic rate (small G) or by L2/DRAM random read-modify-write (G >> L2); see DESIGN.md.
+// Roofline: nominally HBM (8 B/row for price,quantity) but in practice bound by shared-memory
+// wavefronts (wdb_group_wp), the shared-memory atomic rate (wdb_group, small G) or L2 atomics /
+// DRAM random read-modify-write (large G); see DESIGN.md section 3.4.
 //
 // Host-supplied macros: WDB_BLOCK, WDB_UNROLL, WDB_VEC, WDB_NEEDS, WDB_SMEM_SLOTS (0 or power of
-// two), WDB_SMEM_LOG2, WDB_SMEM_PROBES, WDB_HAS_COND; generated WDB_VAL, WDB_KEY, WDB_COND.
+// two), WDB_SMEM_LOG2, WDB_SMEM_PROBES, WDB_HAS_COND, WDB_DENSE, WDB_WP_IDS (0: no wdb_group_wp),
+// WDB_WP_ILP; generated WDB_VAL, WDB_KEY, WDB_COND.
 
 #if WDB_SMEM_SLOTS > 0
 struct wdb_smem_table {
