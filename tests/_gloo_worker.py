@@ -17,7 +17,8 @@ from warpdb_b200.sharded import ShardedDB, shard_range  # noqa: E402
 
 CUDA2TEXT = {"(price[idx] * 0.9f)": "price * 0.9", "(price[idx] > 20.0f)": "price > 20", "price[idx]": "price",
              "quantity[idx]": "quantity", "((price[idx] * quantity[idx]) * 1.08f)": "price * quantity * 1.08",
-             "k[idx]": "k", "v[idx]": "v", None: None}
+             "k[idx]": "k", "v[idx]": "v", None: None, "(price[idx] > 1000000.0f)": "price > 1000000",
+             "(quantity[idx] < (0.0f - 40.0f))": "quantity < 0 - 40", "(quantity[idx] * 0)": "quantity * 0"}
 
 
 def npy(table):
@@ -99,6 +100,16 @@ def main():
             np.testing.assert_allclose(g["vals"].numpy(), r["vals"], rtol=1e-6)
         gd = db.group_agg("price[idx]", "quantity[idx]", None, agg=agg, order=wc.ORDER_KEY_DESC, strategy="exchange")
         assert np.array_equal(gd["keys"].numpy(), orc.group_agg("price", "quantity", None, full, agg=agg, order=orc.ORDER_KEY_DESC)["keys"])
+    # range-partitioned exchange on awkward inputs: no group anywhere; groups on one rank only (the other
+    # ranks send empty pieces); one group; a skewed key range (most keys in the first owner's slice)
+    g = db.group_agg("price[idx]", "quantity[idx]", "(price[idx] > 1000000.0f)", agg=wc.SUM, strategy="exchange")
+    assert g["keys"].numel() == 0
+    r = orc.group_agg("price", "quantity", "quantity < 0 - 40", full, agg=wc.AVG)
+    g = db.group_agg("price[idx]", "quantity[idx]", "(quantity[idx] < (0.0f - 40.0f))", agg=wc.AVG, strategy="exchange")
+    assert np.array_equal(g["keys"].numpy(), r["keys"]) and np.array_equal(g["counts"].numpy(), r["counts"])
+    r = orc.group_agg("price", "quantity * 0", None, full, agg=wc.COUNT)
+    g = db.group_agg("price[idx]", "(quantity[idx] * 0)", None, agg=wc.COUNT, strategy="exchange")
+    assert g["keys"].tolist() == [0] and np.array_equal(g["vals"].numpy(), r["vals"])
     # ORDER BY ... LIMIT: ties (quantity has many) keep global row order
     for desc in (True, False):
         want = orc.query_sql(f"SELECT price FROM t ORDER BY quantity {'DESC' if desc else 'ASC'} LIMIT 7 OFFSET 2", full)

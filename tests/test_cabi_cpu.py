@@ -83,6 +83,36 @@ def test_compact_kernels(tmp_path):
         wc.set_option("compact.variant", None)
 
 
+def test_group_kernels_by_accumulator_layout(tmp_path):
+    """GROUP BY layouts: the narrow-range kernel updates warp-private accumulators with
+    plain LDS/STS -- no shared-memory atomic anywhere in it; the wide-range layout is one native RED
+    per row into the direct-addressed table; the general kernel uses shared CAS + global RED."""
+    def fn_sass(sass, name):
+        part = sass.split("Function : " + name + "\n")[1]
+        return part.split("Function : ")[0]
+    try:
+        wc.set_option("group.debug_span", 1000)          # key range [0, 1000) known
+        src, cubin = wc.debug_compile("group", SCHEMA, "price[idx]", "quantity[idx]", None, wc.SUM)
+        wp = fn_sass(sass_of(cubin, tmp_path, "g_wp.cubin"), "wdb_group_wp")
+        # the only ATOMS left are the shared-memory branch of the generic fp64 atomicAdd on the GLOBAL tables
+        # (fold / spill path, once per key and CTA); the per-row path is LDS / DADD / STS
+        assert wp.count("ATOMS") <= 4 and "ATOMS.ADD" not in wp and wp.count("LDS.64") > 16 and wp.count("STS.64") > 16 and "DADD" in wp
+        assert re.search(r"LDG\.E\.NA\.\w+\.256", wp)
+        assert re.search(r"(ATOMG?|REDG?)\.E\.ADD\.F64", wp)   # the per-CTA totals go to the direct-addressed side table
+        wc.set_option("group.debug_span", 10_000_000)    # wide range: direct-addressed table, no wdb_group_wp
+        src, cubin = wc.debug_compile("group", SCHEMA, "price[idx]", "quantity[idx]", None, wc.SUM)
+        sass = sass_of(cubin, tmp_path, "g_dense.cubin")
+        assert "wdb_group_wp" not in sass and "#define WDB_DENSE 1" in src
+        g = fn_sass(sass, "wdb_group")
+        assert "REDG.E.ADD.F64" in g and "LDG.E.NA.EFL2.256" in g   # evict-first column stream next to the L2-resident table
+        wc.set_option("group.debug_span", 0)             # unknown range: shared-memory table with CAS, global RED behind it
+        src, cubin = wc.debug_compile("group", SCHEMA, "price[idx]", "quantity[idx]", None, wc.SUM)
+        g = fn_sass(sass_of(cubin, tmp_path, "g_hash.cubin"), "wdb_group")
+        assert "ATOMS.CAS" in g and "#define WDB_DENSE 0" in src
+    finally:
+        wc.set_option("group.debug_span", None)
+
+
 def test_keyrange_kernel_evaluates_the_key_expression(tmp_path):
     """Optimizer statistics on demand: min/max of the GROUP BY key expression (kernels/keyrange.cuh)."""
     src, cubin = wc.debug_compile("keyrange", SCHEMA, "(quantity[idx] / 3.0f)")

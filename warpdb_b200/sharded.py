@@ -177,7 +177,8 @@ class ShardedDB:
         pack = torch.zeros(sum(seg), dtype=torch.uint8, device=self.device)
         off = 0
         for i, nb in zip(order, seg):
-            pack[off:off + n * tensors[i].element_size()] = tensors[i].contiguous().view(torch.uint8)
+            if n:
+                pack[off:off + n * tensors[i].element_size()] = tensors[i].reshape(-1).contiguous().view(torch.uint8)
             off += nb
         bufs = [torch.empty_like(pack) for _ in range(self.world)]
         dist.all_gather(bufs, pack, group=self.group)
