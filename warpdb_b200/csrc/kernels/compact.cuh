@@ -467,7 +467,6 @@ wdb_scatter(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2,
   __shared__ float s_stage2[WDB_NWARPS][WDB_WARP_ROWS];
 #endif
   const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const u32 lt = wdb_lanemask_lt();
   const i64 chunk = (i64)blockIdx.x * WDB_NWARPS + warp;
   if (chunk >= nchunks) return;
   if (WDB_CHUNK_DEAD(chunk)) return;
@@ -655,7 +654,6 @@ wdb_compact_l2(const wdb_cols C, float *__restrict__ out, float *__restrict__ ou
   __shared__ i64 s_base;
   __shared__ u32 s_slab;
   const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const u32 lt = wdb_lanemask_lt();
   while (true) {
     if (threadIdx.x == 0) s_slab = atomicAdd(ticket, 1u);
     __syncthreads();                                            // (1)
