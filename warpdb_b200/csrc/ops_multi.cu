@@ -114,23 +114,40 @@ static int run_shard(ShardJob *job, const wdb_col_t *h_cols, int ncols, const ch
 template <class T>
 __global__ void __launch_bounds__(256) minmax_kernel(const T *__restrict__ v, long long n, double *__restrict__ out /* [2*grid] */) {
   double lo = 1.0 / 0.0, hi = -1.0 / 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double x = (double)v[i];
+  auto take = [&](T raw) {
+    const double x = (double)raw;
     lo = x < lo ? x : lo;
     hi = x > hi ? x : hi;
-  }
-  __shared__ double s_lo[256], s_hi[256];
-  s_lo[threadIdx.x] = lo;
-  s_hi[threadIdx.x] = hi;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      s_lo[threadIdx.x] = fmin(s_lo[threadIdx.x], s_lo[threadIdx.x + o]);
-      s_hi[threadIdx.x] = fmax(s_hi[threadIdx.x], s_hi[threadIdx.x + o]);
+  };
+  long long done = 0;
+  if constexpr (sizeof(T) == 4) {   // 128-bit loads over the aligned body
+    if ((reinterpret_cast<unsigned long long>(v) & 15ull) == 0) {
+      const uint4 *p = reinterpret_cast<const uint4 *>(v);
+      const long long nvec = n >> 2;
+      for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nvec; k += (long long)gridDim.x * blockDim.x) {
+        const uint4 q = __ldg(p + k);
+        take(*reinterpret_cast<const T *>(&q.x));
+        take(*reinterpret_cast<const T *>(&q.y));
+        take(*reinterpret_cast<const T *>(&q.z));
+        take(*reinterpret_cast<const T *>(&q.w));
+      }
+      done = nvec << 2;
     }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) { out[2 * blockIdx.x] = s_lo[0]; out[2 * blockIdx.x + 1] = s_hi[0]; }
+  for (long long i = done + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) take(v[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ double s_lo[8], s_hi[8];
+  if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < 8; ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
+    out[2 * blockIdx.x] = lo;
+    out[2 * blockIdx.x + 1] = hi;
+  }
 }
 }  // namespace wdb
 

@@ -33,36 +33,55 @@ template <class T> __device__ __forceinline__ double as_compared(T x) { return (
 template <> __device__ __forceinline__ double as_compared<float>(float x) { return (double)x; }
 template <> __device__ __forceinline__ double as_compared<double>(double x) { return x; }
 
+// One WARP per zone (8 zones per CTA: a CTA per 16 KB zone is launch-bound).  4-byte columns whose
+// zone is complete and 16-byte aligned are read with 128-bit loads, 8 in flight per lane; anything
+// else takes the scalar loop.  Reduction with shuffles only: no shared memory, no block barrier.
 template <class T>
-__global__ void __launch_bounds__(256) zonemap_build_kernel(const T *__restrict__ v, long long n, int zshift,
+__global__ void __launch_bounds__(256) zonemap_build_kernel(const T *__restrict__ v, long long n, int zshift, long long nzones,
                                                             double *__restrict__ mins, double *__restrict__ maxs) {
-  const long long zone = blockIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  const long long zone = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (zone >= nzones) return;                       // warp-uniform
   const long long b = zone << zshift, e = min(b + (1ll << zshift), n);
   double lo = 1.0 / 0.0, hi = -1.0 / 0.0;
   bool nan = false;
-  for (long long i = b + threadIdx.x; i < e; i += 256) {
-    const double x = as_compared<T>(v[i]);
+  auto take = [&](T raw) {
+    const double x = as_compared<T>(raw);
     nan |= (x != x);
     lo = x < lo ? x : lo;
     hi = x > hi ? x : hi;
-  }
-  __shared__ double s_lo[256], s_hi[256];
-  __shared__ int s_nan;
-  if (threadIdx.x == 0) s_nan = 0;
-  s_lo[threadIdx.x] = lo;
-  s_hi[threadIdx.x] = hi;
-  __syncthreads();
-  if (nan) s_nan = 1;
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      s_lo[threadIdx.x] = fmin(s_lo[threadIdx.x], s_lo[threadIdx.x + o]);
-      s_hi[threadIdx.x] = fmax(s_hi[threadIdx.x], s_hi[threadIdx.x + o]);
+  };
+  bool vectorised = false;
+  if constexpr (sizeof(T) == 4) {
+    if (((e - b) & 1023) == 0 && (reinterpret_cast<unsigned long long>(v + b) & 15ull) == 0) {   // whole rounds of 8 x 32 x 4 rows
+      vectorised = true;
+      const uint4 *p = reinterpret_cast<const uint4 *>(v + b);
+      const long long nvec = (e - b) >> 2;
+      for (long long k0 = 0; k0 < nvec; k0 += 256) {
+        uint4 q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) q[u] = __ldg(p + k0 + u * 32 + lane);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          take(*reinterpret_cast<const T *>(&q[u].x));
+          take(*reinterpret_cast<const T *>(&q[u].y));
+          take(*reinterpret_cast<const T *>(&q[u].z));
+          take(*reinterpret_cast<const T *>(&q[u].w));
+        }
+      }
     }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) {   // a zone holding a NaN is never pruned
-    mins[zone] = s_nan ? -1.0 / 0.0 : s_lo[0];
-    maxs[zone] = s_nan ? 1.0 / 0.0 : s_hi[0];
+  if (!vectorised)
+    for (long long i = b + lane; i < e; i += 32) take(v[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  nan = __any_sync(0xffffffffu, nan);
+  if (lane == 0) {   // a zone holding a NaN is never pruned
+    mins[zone] = nan ? -1.0 / 0.0 : lo;
+    maxs[zone] = nan ? 1.0 / 0.0 : hi;
   }
 }
 
@@ -117,12 +136,12 @@ int wdb_zonemap_build(int device, void *stream, const wdb_col_t *col, int64_t zo
   z->maxs = z->mins + std::max<int64_t>(z->nzones, 1);
   cudaStream_t s = (cudaStream_t)stream;
   if (z->nzones > 0) {
-    const unsigned g = (unsigned)z->nzones;
+    const unsigned g = (unsigned)((z->nzones + 7) / 8);
     switch (col->dtype) {
-    case WDB_INT32: zonemap_build_kernel<int><<<g, 256, 0, s>>>((const int *)col->dptr, col->len, z->zshift, z->mins, z->maxs); break;
-    case WDB_INT64: zonemap_build_kernel<long long><<<g, 256, 0, s>>>((const long long *)col->dptr, col->len, z->zshift, z->mins, z->maxs); break;
-    case WDB_FLOAT32: zonemap_build_kernel<float><<<g, 256, 0, s>>>((const float *)col->dptr, col->len, z->zshift, z->mins, z->maxs); break;
-    default: zonemap_build_kernel<double><<<g, 256, 0, s>>>((const double *)col->dptr, col->len, z->zshift, z->mins, z->maxs); break;
+    case WDB_INT32: zonemap_build_kernel<int><<<g, 256, 0, s>>>((const int *)col->dptr, col->len, z->zshift, z->nzones, z->mins, z->maxs); break;
+    case WDB_INT64: zonemap_build_kernel<long long><<<g, 256, 0, s>>>((const long long *)col->dptr, col->len, z->zshift, z->nzones, z->mins, z->maxs); break;
+    case WDB_FLOAT32: zonemap_build_kernel<float><<<g, 256, 0, s>>>((const float *)col->dptr, col->len, z->zshift, z->nzones, z->mins, z->maxs); break;
+    default: zonemap_build_kernel<double><<<g, 256, 0, s>>>((const double *)col->dptr, col->len, z->zshift, z->nzones, z->mins, z->maxs); break;
     }
     stats().launches++;
     if (cudaGetLastError() != cudaSuccess) { cudaFree(z->mins); delete z; return fail("CUDA error: zone map build failed"); }
