@@ -557,7 +557,9 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   const int64_t span = range.known ? range.hi - range.lo + 1 : -1;
   const bool want_wp = wp_fits(t->needs, span);
   // (between the two, contention on few L2 addresses makes the hash table with its bigger footprint the faster one: measured 120 vs 88 Grows/s at 10 K keys)
-  const bool want_dense = sumcnt && !want_wp && span >= opt("group.dense_min_span", 32768) && span <= opt("group.dense_max_span", 1 << 26);
+  // ... and only where the table is not absurdly larger than the rows that will land in it (16 B per key of the range)
+  const bool want_dense = sumcnt && !want_wp && span >= opt("group.dense_min_span", 32768) && span <= opt("group.dense_max_span", 1 << 26) &&
+                          (span <= (1 << 20) || span <= 4 * n || (t->dense_live && (int64_t)t->T.dspan >= span));
   // the warp-private kernel folds its per-CTA totals into a (tiny) direct-addressed table as well (SUM /
   // COUNT / AVG; extrema go to the hash table): the result is then in key order without a sort.  A small
   // side table is a bad target for row-by-row atomics though (few L2 lines take them all), so any other
@@ -636,7 +638,7 @@ int wdb_agg_merge(wdb_agg_t *t, void *stream, const int32_t *d_keys, const doubl
   // this table (wdb_agg_set_key_range) open a side table for the partials as they would for rows
   if (!t->dense_live && t->have_range && (needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0) {
     const int64_t span = t->key_hi - t->key_lo + 1;
-    if (span >= 1 && span <= opt("group.dense_max_span", 1 << 26) && wdb::dense_prepare(t, s, t->key_lo, span)) return 1;
+    if (span >= 1 && span <= opt("group.dense_max_span", 1 << 26) && (span <= (1 << 16) || span <= 16 * m) && wdb::dense_prepare(t, s, t->key_lo, span)) return 1;
   }
 #define WDB_MERGE_CASE(N) case N: agg_merge_kernel<N><<<g, 256, 0, s>>>(t->T, d_keys, d_sums, (const long long *)d_counts, d_mins, d_maxs, (const long long *)d_first, m); break;
   switch (needs) {
