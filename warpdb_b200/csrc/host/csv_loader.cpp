@@ -87,6 +87,22 @@ void cuda_or_throw(cudaError_t e, const char *what) {
 }
 }  // namespace
 
+// HostTable::price / ::quantity (legacy view, see csv_loader.hpp)
+static void fill_legacy_view(HostTable &t) {
+  auto to_vec = [](const HostColumn *c, auto &out) {
+    if (!c) return;
+    std::visit([&](const auto &v) {
+      using E = typename std::decay_t<decltype(v)>::value_type;
+      if constexpr (!std::is_same_v<E, std::string>) {
+        out.clear();
+        for (const auto &x : v) out.push_back(static_cast<typename std::decay_t<decltype(out)>::value_type>(x));
+      }
+    }, c->data);
+  };
+  to_vec(t.get_column("price"), t.price);
+  to_vec(t.get_column("quantity"), t.quantity);
+}
+
 HostTable load_csv_to_host(const std::string &filepath, const std::vector<DataType> &schema) {
   std::ifstream file(filepath);
   if (!file.is_open()) {
@@ -105,6 +121,7 @@ HostTable load_csv_to_host(const std::string &filepath, const std::vector<DataTy
     if (line.empty()) continue;
     append_row(t, line);
   }
+  fill_legacy_view(t);
   return t;
 }
 

@@ -46,6 +46,11 @@ struct HostTable {
   std::vector<HostColumn> columns;
   int num_rows() const;
   const HostColumn *get_column(const std::string &name) const;
+  // Legacy two-column view that the reference's own tests/sql_features_test.cpp still uses
+  // (`h.price[i]`, `h.quantity[i]`); filled by load_csv_to_host / load_json_to_host when columns of
+  // these names exist.  Not read by anything in this library.
+  std::vector<float> price;
+  std::vector<int> quantity;
 };
 
 HostTable load_csv_to_host(const std::string &filepath, const std::vector<DataType> &schema = {});
