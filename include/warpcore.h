@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define WDB_ABI_VERSION 1
+#define WDB_ABI_VERSION 2
 
 /* DataType, in the enum order of include/csv_loader.hpp:13 */
 enum { WDB_INT32 = 0, WDB_INT64 = 1, WDB_FLOAT32 = 2, WDB_FLOAT64 = 3, WDB_STRING = 4 };
@@ -175,6 +175,51 @@ int wdb_multi_project_filter_host(int ndev, const int *devices, const wdb_col_t 
                                   int64_t *h_count);
 /* shard [start,end) of device dev: src/multi_gpu_utils.cpp:24-31 */
 int wdb_shard_range(int64_t n, int ndev, int dev, int64_t *start, int64_t *end);
+
+/* ---- sharded operators with the cross-GPU merge inside the core.
+ * The reference's multi-GPU driver (src/multi_gpu_utils.cpp:5-63, src/warpdb.cpp:508-542) can only
+ * project / filter and moves every shard's output through the host; these entry points keep the
+ * row-range shards (chunk = ceil(n/ndev), :24-31) resident on their GPUs and merge partial
+ * aggregates / top-k candidates GPU to GPU with NCCL over NVLink.
+ *
+ * A communicator binds one GPU to a group of `nranks` GPUs.  One process per GPU: rank 0 calls
+ * wdb_comm_unique_id, the 128 bytes travel by any means (torch.distributed, MPI, a file) and every
+ * rank calls wdb_comm_init_rank.  One process driving all GPUs (the reference's shape):
+ * wdb_comm_init_all fills out[0..ndev) and each communicator is then used from its own host thread.
+ * nranks == 1 needs neither an id nor NCCL. */
+typedef struct wdb_comm wdb_comm_t;
+int wdb_comm_unique_id(void *id128);
+int wdb_comm_init_rank(int device, int nranks, int rank, const void *id128, wdb_comm_t **out);
+int wdb_comm_init_all(int ndev, const int *devices, wdb_comm_t **out);
+int wdb_comm_destroy(wdb_comm_t *c);
+int wdb_comm_info(const wdb_comm_t *c, int *rank, int *nranks, int *device);
+/* wdb_project_filter on this rank's shard (no data-path collective: results stay sharded, rank order is
+ * row order) plus an all-gather of one count per rank: count3 = {rows written by this rank, global
+ * offset of its first row, global total}.  d_count3 (device) / h_count3 (host, synchronises) optional. */
+int wdb_multi_project_filter(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int ncols, const char *expr, const char *cond,
+                             float *d_out, int64_t n_local, int mode, int64_t *d_count3, int64_t *h_count3);
+/* GROUP BY over all shards (jit_group_sum + the std::map merge, src/jit.cpp:179-246, src/warpdb.cpp:373-437):
+ * cols hold this rank's shard (n_local rows, the first one being global row row_base); every rank ends
+ * with the same final groups in d_keys / d_vals (capacity cap) and their number in *d_groups (device)
+ * and *h_groups (host; synchronises; NULL = fully asynchronous).  range_known != 0: every key of every
+ * shard lies in [key_lo, key_hi] (TableStats of the key column); otherwise the core measures it. */
+int wdb_multi_group_agg(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int ncols, const char *val_expr, const char *key_expr,
+                        const char *cond, int agg, int order, int64_t n_local, int64_t row_base, int64_t expected_groups,
+                        int range_known, int64_t key_lo, int64_t key_hi, int32_t *d_keys, float *d_vals, int64_t cap,
+                        int64_t *d_groups, int64_t *h_groups);
+/* ORDER BY key [DESC] LIMIT k OFFSET offset over all shards (jit_sort_float + truncate, src/jit.cpp:283-307,
+ * src/warpdb.cpp:483-495): every rank ends with the same min(k, survivors - offset) values; ties keep
+ * global row order.  *d_n (device) / *h_n (host; synchronises) receive the number of values. */
+int wdb_multi_topk(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int ncols, const char *key_expr, const char *val_expr,
+                   const char *cond, int descending, int64_t k, int64_t offset, int64_t n_local, int64_t row_base,
+                   float *d_out_vals, float *d_out_keys, int64_t *d_n, int64_t *h_n);
+/* Host columns in, host results out, one process driving ndev GPUs (<= 0: all) from one thread per
+ * device: the aggregate / ORDER BY counterparts of wdb_multi_project_filter_host. */
+int wdb_multi_group_agg_host(int ndev, const int *devices, const wdb_col_t *h_cols, int ncols, const char *val_expr, const char *key_expr,
+                             const char *cond, int agg, int order, int64_t n, int64_t expected_groups, int32_t *h_keys, float *h_vals,
+                             int64_t cap, int64_t *h_groups);
+int wdb_multi_topk_host(int ndev, const int *devices, const wdb_col_t *h_cols, int ncols, const char *key_expr, const char *val_expr,
+                        const char *cond, int descending, int64_t k, int64_t offset, int64_t n, float *h_out_vals, int64_t *h_n);
 
 /* ---- synthetic columns for benchmarks/tests (counter based, bit-identical to the oracle's
  * orc_synth_*; not part of the reference) */

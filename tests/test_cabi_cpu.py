@@ -33,7 +33,7 @@ def test_header_symbols_exported():
     L = wc.lib()
     for s in declared:
         assert hasattr(L, s), s
-    assert L.wdb_abi_version() == 1
+    assert L.wdb_abi_version() == 2   # 2: wdb_comm_* / wdb_multi_* (merges inside the core)
 
 
 def test_shard_range_matches_reference_formula():

@@ -25,6 +25,8 @@ SYMBOLS = [
     "wdb_topk", "wdb_sort_float", "wdb_sort_pairs", "wdb_column_minmax", "wdb_multi_project_filter_host",
     "wdb_zonemap_build", "wdb_zonemap_destroy", "wdb_zonemap_info", "wdb_project_filter_pruned",
     "wdb_shard_range", "wdb_synth_f32", "wdb_synth_i32", "wdb_debug_compile", "wdb_free",
+    "wdb_comm_unique_id", "wdb_comm_init_rank", "wdb_comm_init_all", "wdb_comm_destroy", "wdb_comm_info",
+    "wdb_multi_project_filter", "wdb_multi_group_agg", "wdb_multi_topk", "wdb_multi_group_agg_host", "wdb_multi_topk_host",
 ]
 
 
@@ -94,6 +96,16 @@ def lib():
     L.wdb_synth_i32.argtypes = [ci, vp, vp, i64, C.c_uint64, C.c_int32, C.c_int32, i64]
     L.wdb_debug_compile.argtypes = [cp, PC, ci, cp, cp, cp, ci, cp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.wdb_free.argtypes = [vp]
+    L.wdb_comm_unique_id.argtypes = [vp]
+    L.wdb_comm_init_rank.argtypes = [ci, ci, ci, vp, C.POINTER(vp)]
+    L.wdb_comm_init_all.argtypes = [ci, C.POINTER(ci), C.POINTER(vp)]
+    L.wdb_comm_destroy.argtypes = [vp]
+    L.wdb_comm_info.argtypes = [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
+    L.wdb_multi_project_filter.argtypes = [vp, vp, PC, ci, cp, cp, vp, i64, ci, vp, P64]
+    L.wdb_multi_group_agg.argtypes = [vp, vp, PC, ci, cp, cp, cp, ci, ci, i64, i64, i64, ci, i64, i64, vp, vp, i64, vp, P64]
+    L.wdb_multi_topk.argtypes = [vp, vp, PC, ci, cp, cp, cp, ci, i64, i64, i64, i64, vp, vp, vp, P64]
+    L.wdb_multi_group_agg_host.argtypes = [ci, C.POINTER(ci), PC, ci, cp, cp, cp, ci, ci, i64, i64, vp, vp, i64, P64]
+    L.wdb_multi_topk_host.argtypes = [ci, C.POINTER(ci), PC, ci, cp, cp, cp, ci, i64, i64, i64, vp, P64]
     _lib = L
     return L
 

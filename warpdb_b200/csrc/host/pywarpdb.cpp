@@ -63,6 +63,8 @@ PYBIND11_MODULE(pywarpdb, m) {
       .def("query_sql", &WarpDB::query_sql, py::arg("sql"))
       .def("query_multi_gpu", &WarpDB::query_multi_gpu, py::arg("expr"),
            "Execute expression using all available GPUs on the current table.")
+      .def("query_sql_multi_gpu", &WarpDB::query_sql_multi_gpu, py::arg("sql"),
+           "query_sql over all GPUs: partial aggregates / top-k candidates are merged GPU to GPU (NCCL).")
       .def_static("query_multi_gpu_csv", &WarpDB::query_multi_gpu_csv, py::arg("csv_path"), py::arg("expr"),
                   py::arg("rows_per_chunk") = 1000000, "Stream a CSV file in chunks across all GPUs and return results.")
       .def("query_arrow",

@@ -499,6 +499,46 @@ std::vector<float> WarpDB::query_multi_gpu(const std::string &expr) {
   return run_multi_gpu_jit_host(host_table_, p.expr_cuda, p.cond_cuda);
 }
 
+std::vector<float> WarpDB::query_sql_multi_gpu(const std::string &sql) {
+  if (host_table_.num_rows() == 0) throw std::runtime_error("Host table not available for multi-GPU query");
+  QueryAST ast;
+  try {
+    ast = parse_query_extended(tokenize(sql));
+  } catch (const std::exception &e) {
+    throw std::runtime_error(std::string("Failed to parse SQL: ") + e.what());
+  }
+  std::unordered_set<std::string> cols;
+  for (const auto &c : host_table_.columns) cols.insert(c.name);
+  for (const auto &e : ast.select_list) validate_ast(e.get(), cols);
+  if (ast.where) validate_ast(ast.where->get(), cols);
+  if (ast.group_by)
+    for (const auto &k : ast.group_by->keys) validate_ast(k.get(), cols);
+  if (ast.order_by) validate_ast(ast.order_by->expr.get(), cols);
+  if (ast.select_list.empty()) throw std::runtime_error("Empty select list");
+  if (ast.having || ast.distinct) throw std::runtime_error("HAVING and DISTINCT are not supported on the multi-GPU path");
+  refresh_udf_source();
+  const std::string cond = ast.where ? (*ast.where)->to_cuda_expr() : std::string();
+  std::vector<float> result;
+  if (ast.group_by) {
+    auto *agg = dynamic_cast<AggregationNode *>(ast.select_list[0].get());
+    if (!agg) throw std::runtime_error("Only aggregation queries supported with GROUP BY");
+    if (ast.group_by->keys.size() != 1) throw std::runtime_error("the multi-GPU path groups by one key");
+    result = run_multi_gpu_group_host(host_table_, agg->expr->to_cuda_expr(), ast.group_by->keys[0]->to_cuda_expr(), cond, agg->agg,
+                                      ast.order_by && !ast.order_by->ascending).vals;
+    apply_offset_limit(result, ast);
+    return result;
+  }
+  const std::string sel = ast.select_list[0]->to_cuda_expr();
+  if (ast.order_by) {
+    if (!ast.limit) throw std::runtime_error("ORDER BY on the multi-GPU path needs a LIMIT");
+    return run_multi_gpu_topk_host(host_table_, ast.order_by->expr->to_cuda_expr(), sel, cond, !ast.order_by->ascending,
+                                   std::max(ast.limit->count, 0), ast.offset ? std::max(ast.offset->count, 0) : 0);
+  }
+  result = run_multi_gpu_compact_host(host_table_, sel, cond);
+  apply_offset_limit(result, ast);
+  return result;
+}
+
 std::vector<float> WarpDB::query_multi_gpu_csv(const std::string &csv_path, const std::string &expr, int rows_per_chunk) {
   std::ifstream file(csv_path);
   if (!file.is_open()) throw std::runtime_error("Failed to open file: " + csv_path);   // :573-575

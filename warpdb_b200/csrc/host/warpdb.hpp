@@ -27,6 +27,11 @@ public:
   std::vector<float> query_sql(const std::string &sql);
   // same as query() over every visible GPU (row-range shards of the host copy of the table)
   std::vector<float> query_multi_gpu(const std::string &expr);
+  // query_sql() over every visible GPU: GROUP BY aggregates and ORDER BY ... LIMIT run on row-range
+  // shards and are merged GPU to GPU inside the core (NCCL over NVLink); plain SELECT compacts per
+  // shard.  HAVING / DISTINCT are not offered on this path.  Not in the reference (src/warpdb.cpp:508-542
+  // shards query() only).
+  std::vector<float> query_sql_multi_gpu(const std::string &sql);
   // stream a CSV in chunks of rows_per_chunk rows through all GPUs
   static std::vector<float> query_multi_gpu_csv(const std::string &csv_path, const std::string &expr, int rows_per_chunk = 1000000);
   // query() exported through the Arrow C data interface

@@ -59,8 +59,8 @@ __device__ __forceinline__ void wdb_group_row(const wdb_table &T,
     const u32 di = (u32)key - (u32)T.dlo;
     if (di < T.dspan) {
       if (di >= pass_bits && di < pass) {
-        if (WDB_NEEDS & WDB_NEED_SUM_BIT) atomicAdd(&T.dsums[di], dv + 0.0);
-        if (WDB_NEEDS & WDB_NEED_CNT_BIT) atomicAdd(&T.dcnts[di], 1ull);
+        const i64 e = (WDB_NEEDS & WDB_NEED_MINMAX_BIT) ? wdb_f64_enc(dv) : 0;
+        wdb_dense_add<WDB_NEEDS & 7>(T, di, dv, 1ull, e, e);
       }
       return;
     }
@@ -399,9 +399,8 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
     const int key = (int)((u32)key_base + id);
 #if WDB_DENSE
     const u32 di = (u32)key - (u32)T.dlo;     // the host made the direct-addressed side table cover [key_base, key_base + WDB_WP_IDS)
-    if (di < T.dspan && !WDB_WP_HAS_MM && !WDB_WP_HAS_FIRST) {   // the side table holds sums and counts only
-      if (WDB_WP_HAS_SUM) atomicAdd(&T.dsums[di], sum + 0.0);
-      if (WDB_WP_HAS_CNT) atomicAdd(&T.dcnts[di], cnt);
+    if (di < T.dspan && !WDB_WP_HAS_FIRST) {   // the side table holds sums, counts and extrema
+      wdb_dense_add<WDB_NEEDS & 7>(T, di, sum, cnt, mn, mx);
       continue;
     }
 #endif

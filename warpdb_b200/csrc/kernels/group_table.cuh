@@ -6,7 +6,9 @@
 // holds the key equal to the empty-slot sentinel INT_MIN):
 //   keys[cap+1] int32 (INT_MIN = empty)   sums[cap+1] f64   counts[cap+1] u64
 //   mins/maxs[cap+1] order-preserving i64 encodings of f64   first[cap+1] i64 (smallest row id)
-//   meta[0] = groups inserted, meta[1] = overflow flag, meta[2] = special slot used
+//   meta[0] = groups inserted, meta[1] = overflow flag, meta[2] = special slot used,
+//   meta[3] = rows that bypassed the shared-memory accumulators, meta[4] = hash entries found outside
+//   the side table's range when the table was folded for a cross-GPU merge (stale statistics)
 #ifndef WDB_GROUP_TABLE_CUH
 #define WDB_GROUP_TABLE_CUH
 
@@ -30,9 +32,14 @@ struct wdb_table {
   // direct-addressed side table for integer keys with a known range (optimizer statistics): key k
   // lives at index k - dlo, no probe and no CAS.  dsums start as -0.0 (WDB_DENSE_EMPTY): adding any
   // value other than -0.0 changes the bit pattern, so an untouched slot is recognisable without a
-  // second atomic; -0.0 addends are added as +0.0.  dspan == 0: not in use.
+  // second atomic; -0.0 addends are added as +0.0.  dmins / dmaxs hold order-preserving encodings
+  // (+inf / -inf when untouched).  Only the arrays the table's needs call for exist.  dspan == 0: not
+  // in use.  Identical layouts on every GPU make the cross-GPU merge one all-reduce per array
+  // (sum / sum / min / max; -0.0 + -0.0 = -0.0 keeps the untouched marker).
   double *dsums;
   unsigned long long *dcnts;
+  long long *dmins;
+  long long *dmaxs;
   int dlo;
   unsigned int dspan;
 };
@@ -49,6 +56,21 @@ __device__ __forceinline__ double wdb_f64_dec(long long e) {
 }
 #define WDB_ENC_PLUS_INF 0x7ff0000000000000ll
 #define WDB_ENC_MINUS_INF (-0x7ff0000000000000ll)
+
+// one row (or one partial aggregate) into entry di of the direct-addressed side table
+template <int NEEDS>
+__device__ __forceinline__ void wdb_dense_add(const wdb_table &T, unsigned int di, double sum, unsigned long long cnt,
+                                              long long mn_enc, long long mx_enc) {
+  if (NEEDS & WDB_NEED_SUM_BIT) atomicAdd(&T.dsums[di], sum + 0.0);
+  if (NEEDS & WDB_NEED_CNT_BIT) atomicAdd(&T.dcnts[di], cnt);
+  if (NEEDS & WDB_NEED_MINMAX_BIT) { atomicMin(&T.dmins[di], mn_enc); atomicMax(&T.dmaxs[di], mx_enc); }
+}
+// has entry i been touched?  (every row updates every accumulator the table tracks)
+template <int NEEDS> __device__ __forceinline__ bool wdb_dense_present(const wdb_table &T, long long i) {
+  if (NEEDS & WDB_NEED_CNT_BIT) return T.dcnts[i] != 0ull;
+  if (NEEDS & WDB_NEED_SUM_BIT) return (unsigned long long)__double_as_longlong(T.dsums[i]) != WDB_DENSE_EMPTY;
+  return T.dmins[i] != WDB_ENC_PLUS_INF || T.dmaxs[i] != WDB_ENC_MINUS_INF;
+}
 
 __device__ __forceinline__ unsigned int wdb_hash32(int key) {
   unsigned int x = (unsigned int)key;

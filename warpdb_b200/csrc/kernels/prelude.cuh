@@ -26,6 +26,12 @@ template <class T> struct wdb_cell {
 
 #define WDB_FULL_MASK 0xffffffffu
 
+// ORDER BY keys: one NaN policy for every path (register top-k, threshold compaction, radix sort):
+// a NaN key orders as the worst key of the direction, after every number (fmaxf / fminf return the
+// non-NaN operand); among themselves and against a real -inf / +inf such rows keep row order.
+__device__ __forceinline__ float wdb_nanlast_d(float k) { return fmaxf(k, __int_as_float(0xff800000)); }
+__device__ __forceinline__ float wdb_nanlast_a(float k) { return fminf(k, __int_as_float(0x7f800000)); }
+
 __device__ __forceinline__ u32 wdb_lane() { u32 l; asm("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
 __device__ __forceinline__ u32 wdb_lanemask_lt() { u32 m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 

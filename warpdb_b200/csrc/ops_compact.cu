@@ -80,7 +80,10 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
   if (unroll < 1 || unroll > 8) return fail("compact.unroll must be in [1,8]");
   const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)vec * 4);
   if (!aligned && variant == 1) variant = 2;       // bulk copies need 16-byte aligned columns
-  if (prune) variant = 2;                          // zone-map pruning is wired into the two-pass kernels
+  if (prune) {                                     // zone-map pruning is wired into the two-pass kernels
+    variant = 2;
+    while (unroll & (unroll - 1)) --unroll;        // a warp's chunk must not straddle zones: power-of-two chunks divide the (power-of-two) zone size
+  }
   size_t row_bytes = 0;
   for (const auto &u : spec.used) row_bytes += dtype_size(u.dtype);
   if (variant != 1)
@@ -117,7 +120,8 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
                    int thresh, float tau, int64_t out_cap, const unsigned char *zmask, int zshift) {
   CompactPlan p;
   if (plan_compact(cols, ncols, expr, expr2, cond, true, thresh, &p, zmask != nullptr)) return 1;
-  if (zmask && (1ll << zshift) < p.tile_rows / (p.block / 32)) return fail("zone size %lld is smaller than a compaction chunk", 1ll << zshift);
+  if (zmask && ((1ll << zshift) < p.tile_rows / (p.block / 32) || (1ll << zshift) % (p.tile_rows / (p.block / 32)) != 0))
+    return fail("zone size %lld is not a multiple of the compaction chunk (%lld rows)", 1ll << zshift, (long long)(p.tile_rows / (p.block / 32)));
   GenSpec &spec = p.spec;
   const int block = p.block;
   const int64_t tile_rows = p.tile_rows;

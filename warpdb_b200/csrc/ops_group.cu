@@ -10,26 +10,12 @@
 #include <cstring>
 
 #include "core.hpp"
-#include "kernels/group_table.cuh"
+#include "agg.hpp"
 
 namespace wdb {
 template <class K>
 int radix_sort(Device *d, cudaStream_t s, K *keys, K *tmp_keys, unsigned *pay, unsigned *tmp_pay, long long n, int key_bits);
 }
-
-struct wdb_agg {
-  wdb::Device *dev = nullptr;
-  int needs = 0;
-  int64_t cap = 0;          // power of two
-  char *mem = nullptr;
-  wdb_table T{};
-  // direct-addressed side table (T.dsums / T.dcnts), allocated on first use
-  char *dense_mem = nullptr;
-  int64_t dense_cap = 0;    // allocated entries
-  bool dense_live = false;  // holds aggregates (T.dspan > 0)
-  bool have_range = false;  // optimizer statistics: every key of the next consume calls lies in [key_lo, key_hi]
-  int64_t key_lo = 0, key_hi = -1;
-};
 
 using namespace wdb;
 
@@ -42,7 +28,7 @@ __global__ void agg_init_kernel(wdb_table T, long long slots) {
     T.mins[i] = WDB_ENC_PLUS_INF;
     T.maxs[i] = WDB_ENC_MINUS_INF;
     T.first[i] = 0x7fffffffffffffffll;
-    if (i < 4) T.meta[i] = 0u;
+    if (i < 8) T.meta[i] = 0u;
   }
 }
 
@@ -51,11 +37,11 @@ __global__ void agg_merge_kernel(wdb_table T, const int *__restrict__ keys, cons
                                  const long long *__restrict__ counts, const double *__restrict__ mins,
                                  const double *__restrict__ maxs, const long long *__restrict__ first, long long m) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
-    if ((NEEDS & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0) {   // a live direct-addressed side table owns the keys of its range
+    if ((NEEDS & WDB_NEED_FIRST_BIT) == 0) {   // a live direct-addressed side table owns the keys of its range
       const unsigned di = (unsigned)keys[i] - (unsigned)T.dlo;
       if (di < T.dspan) {
-        if (NEEDS & WDB_NEED_SUM_BIT) atomicAdd(&T.dsums[di], sums[i] + 0.0);
-        if (NEEDS & WDB_NEED_CNT_BIT) atomicAdd(&T.dcnts[di], (unsigned long long)counts[i]);
+        wdb_dense_add<NEEDS & 7>(T, di, (NEEDS & WDB_NEED_SUM_BIT) ? sums[i] : 0.0, (NEEDS & WDB_NEED_CNT_BIT) ? (unsigned long long)counts[i] : 0ull,
+                                 (NEEDS & WDB_NEED_MINMAX_BIT) ? wdb_f64_enc(mins[i]) : 0, (NEEDS & WDB_NEED_MINMAX_BIT) ? wdb_f64_enc(maxs[i]) : 0);
         continue;
       }
     }
@@ -118,15 +104,12 @@ __global__ void agg_emit_kernel(wdb_table T, long long slots, const unsigned *__
 }
 
 // ---- direct-addressed side table -----------------------------------------------------------------
-__global__ void dense_init_kernel(unsigned long long *sums, unsigned long long *cnts, long long span) {
+__global__ void dense_init_kernel(wdb_table T, int needs, long long span) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < span; i += (long long)gridDim.x * blockDim.x) {
-    sums[i] = WDB_DENSE_EMPTY;
-    cnts[i] = 0ull;
+    if (needs & WDB_NEED_SUM_BIT) reinterpret_cast<unsigned long long *>(T.dsums)[i] = WDB_DENSE_EMPTY;
+    if (needs & WDB_NEED_CNT_BIT) T.dcnts[i] = 0ull;
+    if (needs & WDB_NEED_MINMAX_BIT) { T.dmins[i] = WDB_ENC_PLUS_INF; T.dmaxs[i] = WDB_ENC_MINUS_INF; }
   }
-}
-template <int NEEDS> __device__ __forceinline__ bool dense_present(const wdb_table &T, long long i) {
-  if (NEEDS & WDB_NEED_CNT_BIT) return T.dcnts[i] != 0ull;
-  return (unsigned long long)__double_as_longlong(T.dsums[i]) != WDB_DENSE_EMPTY;
 }
 constexpr int kDenseBlock = 256, kDenseItems = 8, kDenseTile = kDenseBlock * kDenseItems;
 // pass 1: present entries per tile of 2048 indices
@@ -136,7 +119,7 @@ template <int NEEDS> __global__ void __launch_bounds__(kDenseBlock) dense_count_
 #pragma unroll
   for (int k = 0; k < kDenseItems; ++k) {
     const long long i = base + (long long)k * kDenseBlock + threadIdx.x;
-    if (i < (long long)T.dspan && dense_present<NEEDS>(T, i)) ++c;
+    if (i < (long long)T.dspan && wdb_dense_present<NEEDS>(T, i)) ++c;
   }
   c = __reduce_add_sync(0xffffffffu, c);
   __shared__ unsigned s[kDenseBlock / 32];
@@ -148,9 +131,9 @@ template <int NEEDS> __global__ void __launch_bounds__(kDenseBlock) dense_count_
     tile_counts[blockIdx.x] = t;
   }
 }
-// pass 2 (one CTA): exclusive scan of the tile counts; total -> *total
+// pass 2 (one CTA): exclusive scan of the tile counts; total -> *total (and, as a signed 64-bit, -> *total_out)
 __global__ void __launch_bounds__(1024) dense_scan_kernel(const unsigned *__restrict__ tile_counts, unsigned long long *__restrict__ tile_offsets,
-                                                           long long ntiles, unsigned long long *__restrict__ total) {
+                                                           long long ntiles, unsigned long long *__restrict__ total, long long *__restrict__ total_out) {
   __shared__ unsigned long long s_warp[32];
   __shared__ unsigned long long s_carry;
   if (threadIdx.x == 0) s_carry = 0ull;
@@ -182,13 +165,18 @@ __global__ void __launch_bounds__(1024) dense_scan_kernel(const unsigned *__rest
     if (threadIdx.x == 1023) s_carry = incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = s_carry;
+  if (threadIdx.x == 0) {
+    *total = s_carry;
+    if (total_out) *total_out = (long long)s_carry;
+  }
 }
 // pass 3: ranked emit in key order (ascending, or descending when desc != 0); `to_table` folds the
-// entries into the hash table instead (flush)
+// entries into the hash table instead (flush).  Groups beyond `cap` are dropped (the caller compares
+// the total with cap).
 template <int NEEDS> __global__ void __launch_bounds__(kDenseBlock)
 dense_emit_kernel(wdb_table T, const unsigned long long *__restrict__ tile_offsets, const unsigned long long *__restrict__ total, int desc, int agg,
-                  int to_table, int *__restrict__ o_keys, float *__restrict__ o_vals, double *__restrict__ o_sums, long long *__restrict__ o_counts) {
+                  int to_table, long long cap, int *__restrict__ o_keys, float *__restrict__ o_vals, double *__restrict__ o_sums,
+                  long long *__restrict__ o_counts, double *__restrict__ o_mins, double *__restrict__ o_maxs) {
   __shared__ unsigned s_wbase[kDenseBlock / 32];
   const long long base = (long long)blockIdx.x * kDenseTile;
   // thread t owns kDenseItems CONSECUTIVE indices so that ranks follow key order
@@ -197,7 +185,7 @@ dense_emit_kernel(wdb_table T, const unsigned long long *__restrict__ tile_offse
 #pragma unroll
   for (int k = 0; k < kDenseItems; ++k) {
     const long long i = base + (long long)threadIdx.x * kDenseItems + k;
-    pres[k] = i < (long long)T.dspan && dense_present<NEEDS>(T, i);
+    pres[k] = i < (long long)T.dspan && wdb_dense_present<NEEDS>(T, i);
     c += pres[k] ? 1u : 0u;
   }
   unsigned x = c;
@@ -219,23 +207,52 @@ dense_emit_kernel(wdb_table T, const unsigned long long *__restrict__ tile_offse
     const int key = (int)((unsigned)T.dlo + (unsigned)i);
     const double sum = (NEEDS & WDB_NEED_SUM_BIT) ? T.dsums[i] : 0.0;
     const unsigned long long cnt = (NEEDS & WDB_NEED_CNT_BIT) ? T.dcnts[i] : 0ull;
+    const long long mn = (NEEDS & WDB_NEED_MINMAX_BIT) ? T.dmins[i] : 0, mx = (NEEDS & WDB_NEED_MINMAX_BIT) ? T.dmaxs[i] : 0;
     if (to_table) {
       const long long sl = wdb_table_slot(T, key);
-      if (sl >= 0) wdb_table_add<NEEDS>(T, sl, sum, cnt, 0, 0, 0);
+      if (sl >= 0) wdb_table_add<NEEDS>(T, sl, sum, cnt, mn, mx, 0);
     } else {
       const unsigned long long o = desc ? g - 1ull - pos : pos;
-      if (o_keys) o_keys[o] = key;
-      if (o_vals) o_vals[o] = agg == WDB_SUM ? (float)sum : (agg == WDB_AVG ? (float)(sum / (double)((NEEDS & WDB_NEED_CNT_BIT) ? cnt : 1ull)) : (float)(double)cnt);   // src/warpdb.cpp:429-435
-      if (o_sums) o_sums[o] = sum;
-      if (o_counts) o_counts[o] = (long long)cnt;
+      if (o < (unsigned long long)cap) {
+        if (o_keys) o_keys[o] = key;
+        if (o_vals) {   // src/warpdb.cpp:429-435: double results narrowed to float
+          float v;
+          switch (agg) {
+          case WDB_SUM: v = (float)sum; break;
+          case WDB_AVG: v = (float)(sum / (double)((NEEDS & WDB_NEED_CNT_BIT) ? cnt : 1ull)); break;
+          case WDB_COUNT: v = (float)(double)cnt; break;
+          case WDB_MIN: v = (float)wdb_f64_dec(mn); break;
+          default: v = (float)wdb_f64_dec(mx); break;
+          }
+          o_vals[o] = v;
+        }
+        if (o_sums) o_sums[o] = sum;
+        if (o_counts) o_counts[o] = (long long)cnt;
+        if (o_mins) o_mins[o] = wdb_f64_dec(mn);
+        if (o_maxs) o_maxs[o] = wdb_f64_dec(mx);
+      }
     }
     ++pos;
+  }
+}
+// hash table -> side table (cross-GPU merge: every GPU's whole partial must sit in the side table);
+// entries outside its range are counted in meta[4]
+template <int NEEDS> __global__ void agg_hash_to_dense_kernel(wdb_table T, long long slots) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (long long)gridDim.x * blockDim.x) {
+    const bool special = i == slots - 1;
+    const bool used = special ? (T.meta[2] != 0u) : (T.keys[i] != WDB_KEY_EMPTY);
+    if (!used) continue;
+    const int key = special ? WDB_KEY_EMPTY : T.keys[i];
+    const unsigned di = (unsigned)key - (unsigned)T.dlo;
+    if (di < T.dspan) wdb_dense_add<NEEDS>(T, di, (NEEDS & WDB_NEED_SUM_BIT) ? T.sums[i] : 0.0, (NEEDS & WDB_NEED_CNT_BIT) ? T.counts[i] : 0ull,
+                                           (NEEDS & WDB_NEED_MINMAX_BIT) ? T.mins[i] : 0, (NEEDS & WDB_NEED_MINMAX_BIT) ? T.maxs[i] : 0);
+    else atomicAdd(&T.meta[4], 1u);
   }
 }
 
 namespace wdb {
 
-static int needs_for_agg(int agg) {
+int needs_for_agg(int agg) {
   switch (agg) {
   case WDB_SUM: return WDB_NEED_SUM_BIT;
   case WDB_AVG: return WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT;
@@ -261,7 +278,6 @@ static bool wp_fits(int needs, int64_t span) {
 }
 
 struct GroupPlan { GenSpec spec; int block, unroll, vec, smem_slots, wp_ids; size_t smem_bytes; const char *entry; };
-struct KeyRange { bool known; int64_t lo, hi; };
 
 static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const char *key, const char *cond, int needs,
                       int64_t cap_hint, KeyRange range, bool dense, bool use_wp, bool check_alignment, GroupPlan *p) {
@@ -346,7 +362,7 @@ int gen_group_source(const wdb_col_t *cols, int ncols, const char *val, const ch
                      std::string *src) {
   GroupPlan p;
   const int64_t span = opt("group.debug_span", 0);   // introspection only: pretend the key range [0, span) is known
-  if (plan_group(cols, ncols, val, key, cond, needs_for_agg(agg), 2048, KeyRange{span > 0, 0, span - 1}, span > 0 && (needs_for_agg(agg) & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0,
+  if (plan_group(cols, ncols, val, key, cond, needs_for_agg(agg), 2048, KeyRange{span > 0, 0, span - 1}, span > 0,
                  wp_fits(needs_for_agg(agg), span), false, &p)) return 1;
   *src = gen_source(p.spec);
   return 0;
@@ -380,7 +396,7 @@ int gen_keyrange_source(const wdb_col_t *cols, int ncols, const char *key, std::
   return 0;
 }
 
-static int auto_key_range(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncols, const char *key_expr, int64_t n, KeyRange *out) {
+int auto_key_range(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncols, const char *key_expr, int64_t n, KeyRange *out) {
   GenSpec spec;
   if (!plan_keyrange(cols, ncols, key_expr, true, &spec)) return 0;
   const int block = kKeyRangeBlock, unroll = kKeyRangeUnroll, vec = kKeyRangeVec;
@@ -417,16 +433,20 @@ static int dense_scratch(wdb_agg *t, cudaStream_t s, DenseScratch *sc) {
   return 0;
 }
 #define WDB_DENSE_DISPATCH(needs, CALL)                                    \
-  switch ((needs) & (WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) {               \
+  switch ((needs) & 7) {                                                   \
   case 1: { constexpr int N = 1; CALL; } break;                            \
   case 2: { constexpr int N = 2; CALL; } break;                            \
-  default: { constexpr int N = 3; CALL; } break;                           \
+  case 3: { constexpr int N = 3; CALL; } break;                            \
+  case 4: { constexpr int N = 4; CALL; } break;                            \
+  case 5: { constexpr int N = 5; CALL; } break;                            \
+  case 6: { constexpr int N = 6; CALL; } break;                            \
+  default: { constexpr int N = 7; CALL; } break;                           \
   }
-// count + scan: tile offsets and the number of present entries (left on the device in sc->total)
-static int dense_rank(wdb_agg *t, cudaStream_t s, DenseScratch *sc) {
+// count + scan: tile offsets and the number of present entries (left on the device in sc->total and, when given, *d_total)
+static int dense_rank(wdb_agg *t, cudaStream_t s, DenseScratch *sc, long long *d_total = nullptr) {
   if (dense_scratch(t, s, sc)) return 1;
   WDB_DENSE_DISPATCH(t->needs, (dense_count_kernel<N><<<(unsigned)sc->ntiles, kDenseBlock, 0, s>>>(t->T, sc->tile_counts)));
-  dense_scan_kernel<<<1, 1024, 0, s>>>(sc->tile_counts, sc->tile_offsets, sc->ntiles, sc->total);
+  dense_scan_kernel<<<1, 1024, 0, s>>>(sc->tile_counts, sc->tile_offsets, sc->ntiles, sc->total, d_total);
   stats().launches += 2;
   WDB_CUDA(cudaGetLastError());
   return 0;
@@ -436,8 +456,8 @@ static int dense_flush(wdb_agg *t, cudaStream_t s) {
   if (!t->dense_live) return 0;
   DenseScratch sc;
   if (dense_rank(t, s, &sc)) return 1;
-  WDB_DENSE_DISPATCH(t->needs, (dense_emit_kernel<N><<<(unsigned)sc.ntiles, kDenseBlock, 0, s>>>(t->T, sc.tile_offsets, sc.total, 0, 0, 1, nullptr, nullptr,
-                                                                                                    nullptr, nullptr)));
+  WDB_DENSE_DISPATCH(t->needs, (dense_emit_kernel<N><<<(unsigned)sc.ntiles, kDenseBlock, 0, s>>>(t->T, sc.tile_offsets, sc.total, 0, 0, 1, 0, nullptr, nullptr,
+                                                                                                    nullptr, nullptr, nullptr, nullptr)));
   stats().launches++;
   WDB_CUDA(cudaGetLastError());
   WDB_CUDA(cudaFreeAsync(sc.buf, s));
@@ -445,33 +465,59 @@ static int dense_flush(wdb_agg *t, cudaStream_t s) {
   t->T.dspan = 0;
   return 0;
 }
+static int64_t dense_bytes_per_key(int needs) {
+  return ((needs & WDB_NEED_SUM_BIT) ? 8 : 0) + ((needs & WDB_NEED_CNT_BIT) ? 8 : 0) + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0);
+}
 // make [lo, lo + span) the live side table (flushing a different live range first)
-static int dense_prepare(wdb_agg *t, cudaStream_t s, int64_t lo, int64_t span) {
+int dense_prepare(wdb_agg *t, cudaStream_t s, int64_t lo, int64_t span) {
+  if (t->needs & WDB_NEED_FIRST_BIT) return fail("internal: a table that tracks first rows has no direct-addressed side table");
   if (t->dense_live && t->T.dlo == (int)lo && (int64_t)t->T.dspan == span) return 0;
   if (t->dense_live && lo >= (int64_t)t->T.dlo && lo + span <= (int64_t)t->T.dlo + (int64_t)t->T.dspan) return 0;   // covered by the live range
   if (dense_flush(t, s)) return 1;
   if (t->dense_cap < span) {
     if (t->dense_mem) { WDB_CUDA(cudaStreamSynchronize(s)); WDB_CUDA(cudaFree(t->dense_mem)); t->dense_mem = nullptr; t->dense_cap = 0; }
-    cudaError_t e = cudaMalloc((void **)&t->dense_mem, (size_t)span * 16 + 64);
+    cudaError_t e = cudaMalloc((void **)&t->dense_mem, (size_t)span * dense_bytes_per_key(t->needs) + 64);
     if (e != cudaSuccess) return fail("CUDA error: %s (direct-addressed aggregation table of %lld entries)", cudaGetErrorString(e), (long long)span);
     t->dense_cap = span;
   }
-  t->T.dsums = (double *)t->dense_mem;
-  t->T.dcnts = (unsigned long long *)(t->dense_mem + (size_t)t->dense_cap * 8);
+  char *p = t->dense_mem;
+  t->T.dsums = (double *)p; p += (t->needs & WDB_NEED_SUM_BIT) ? (size_t)t->dense_cap * 8 : 0;
+  t->T.dcnts = (unsigned long long *)p; p += (t->needs & WDB_NEED_CNT_BIT) ? (size_t)t->dense_cap * 8 : 0;
+  t->T.dmins = (long long *)p; p += (t->needs & WDB_NEED_MINMAX_BIT) ? (size_t)t->dense_cap * 8 : 0;
+  t->T.dmaxs = (long long *)p;
   t->T.dlo = (int)lo;
   t->T.dspan = (unsigned)span;
-  dense_init_kernel<<<grid_for(t->dev, span), 256, 0, s>>>((unsigned long long *)t->T.dsums, t->T.dcnts, span);
+  dense_init_kernel<<<grid_for(t->dev, span), 256, 0, s>>>(t->T, t->needs, span);
   stats().launches++;
   WDB_CUDA(cudaGetLastError());
   t->dense_live = true;
   return 0;
 }
 
-}  // namespace wdb
+int agg_hash_to_dense(wdb_agg *t, cudaStream_t s) {
+  if (!t->dense_live) return fail("internal: no live side table");
+  const long long slots = t->cap + 1;
+  WDB_DENSE_DISPATCH(t->needs, (agg_hash_to_dense_kernel<N><<<grid_for(t->dev, slots), 256, 0, s>>>(t->T, slots)));
+  stats().launches++;
+  WDB_CUDA(cudaGetLastError());
+  return 0;
+}
 
-extern "C" {
+int agg_export_dense_async(wdb_agg *t, cudaStream_t s, int agg, int order, int32_t *d_keys, float *d_vals, double *d_sums,
+                           int64_t *d_counts, double *d_mins, double *d_maxs, int64_t cap, long long *d_groups) {
+  if (!t->dense_live) return fail("internal: no live side table");
+  if (order == WDB_ORDER_FIRST) return fail("internal: the side table cannot export in first-appearance order");
+  DenseScratch sc;
+  if (dense_rank(t, s, &sc, d_groups)) return 1;
+  WDB_DENSE_DISPATCH(t->needs, (dense_emit_kernel<N><<<(unsigned)sc.ntiles, kDenseBlock, 0, s>>>(t->T, sc.tile_offsets, sc.total, order == WDB_ORDER_KEY_DESC, agg, 0,
+                                                                                                    (long long)cap, d_keys, d_vals, d_sums, (long long *)d_counts, d_mins, d_maxs)));
+  stats().launches++;
+  WDB_CUDA(cudaGetLastError());
+  WDB_CUDA(cudaFreeAsync(sc.buf, s));
+  return 0;
+}
 
-int wdb_agg_create(int device, int64_t expected_groups, int needs, wdb_agg_t **out) {
+int agg_create_on(int device, int64_t expected_groups, int needs, cudaStream_t stream, wdb_agg **out) {
   Device *d;
   if (get_device(device, &d)) return 1;
   if (!out) return fail("null output");
@@ -504,8 +550,20 @@ int wdb_agg_create(int device, int64_t expected_groups, int needs, wdb_agg_t **o
     while ((1ll << lg) < cap) ++lg;
     t->T.shift = 32u - lg;
   }
-  if (wdb_agg_reset(t, nullptr)) { cudaFree(t->mem); delete t; return 1; }
+  if (wdb_agg_reset(t, stream)) { cudaFree(t->mem); delete t; return 1; }
   *out = t;
+  return 0;
+}
+
+}  // namespace wdb
+
+extern "C" {
+
+int wdb_agg_create(int device, int64_t expected_groups, int needs, wdb_agg_t **out) {
+  // The table is initialised on the legacy NULL stream; callers consume on streams of their own
+  // (non-blocking streams have no implicit ordering with it), so wait for the initialisation here.
+  if (wdb::agg_create_on(device, expected_groups, needs, nullptr, out)) return 1;
+  WDB_CUDA(cudaStreamSynchronize(nullptr));
   return 0;
 }
 
@@ -553,15 +611,15 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   // Integer keys with a known range: <= wp_max_span -> warp-private shared-memory accumulators;
   // <= dense_max_span -> direct-addressed table in HBM/L2 (no probe, no CAS, ordered export without
   // a sort); otherwise the hash table.
-  const bool sumcnt = (t->needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0;
+  const bool sumcnt = (t->needs & WDB_NEED_FIRST_BIT) == 0;   // what the side table can hold: sums, counts, extrema (not first rows)
   const int64_t span = range.known ? range.hi - range.lo + 1 : -1;
   const bool want_wp = wp_fits(t->needs, span);
   // (between the two, contention on few L2 addresses makes the hash table with its bigger footprint the faster one: measured 120 vs 88 Grows/s at 10 K keys)
   // ... and only where the table is not absurdly larger than the rows that will land in it (16 B per key of the range)
   const bool want_dense = sumcnt && !want_wp && span >= opt("group.dense_min_span", 32768) && span <= opt("group.dense_max_span", 1 << 26) &&
                           (span <= (1 << 20) || span <= 4 * n || (t->dense_live && (int64_t)t->T.dspan >= span));
-  // the warp-private kernel folds its per-CTA totals into a (tiny) direct-addressed table as well (SUM /
-  // COUNT / AVG; extrema go to the hash table): the result is then in key order without a sort.  A small
+  // the warp-private kernel folds its per-CTA totals into a (tiny) direct-addressed table as well:
+  // the result is then in key order without a sort.  A small
   // side table is a bad target for row-by-row atomics though (few L2 lines take them all), so any other
   // kernel folds it into the hash table first.
   const bool wp_side = want_wp && sumcnt;
@@ -601,7 +659,7 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
     return launch(k, grid, p.block, p.smem_bytes, (cudaStream_t)stream, args);
   }
   if (t->dense_live) {   // index slices of the direct-addressed table, each small enough to stay in the L2
-    const double per = ((t->needs & WDB_NEED_SUM_BIT) ? 8.0 : 0.0) + ((t->needs & WDB_NEED_CNT_BIT) ? 8.0 : 0.0);
+    const double per = (double)dense_bytes_per_key(t->needs);
     const double budget = (double)opt("group.dense_l2_budget_mb", 60) * 1048576.0;
     int64_t passes = std::max<int64_t>(1, (int64_t)std::ceil((double)t->T.dspan * per / budget));
     const int64_t forced = opt("group.dense_passes", -1);
@@ -636,7 +694,7 @@ int wdb_agg_merge(wdb_agg_t *t, void *stream, const int32_t *d_keys, const doubl
   cudaStream_t s = (cudaStream_t)stream;
   // partial keys inside the side table's range are added there (one home per key); statistics set on
   // this table (wdb_agg_set_key_range) open a side table for the partials as they would for rows
-  if (!t->dense_live && t->have_range && (needs & ~(WDB_NEED_SUM_BIT | WDB_NEED_CNT_BIT)) == 0) {
+  if (!t->dense_live && t->have_range && (needs & WDB_NEED_FIRST_BIT) == 0) {
     const int64_t span = t->key_hi - t->key_lo + 1;
     if (span >= 1 && span <= opt("group.dense_max_span", 1 << 26) && (span <= (1 << 16) || span <= 16 * m) && wdb::dense_prepare(t, s, t->key_lo, span)) return 1;
   }
@@ -703,7 +761,7 @@ int wdb_agg_export(wdb_agg_t *t, void *stream, int agg, int order, int32_t *d_ke
   if (read_meta(t, s, meta)) return 1;
   if (t->dense_live) {
     const bool hash_empty = meta[0] == 0 && meta[2] == 0;
-    if (hash_empty && order != WDB_ORDER_FIRST && !d_mins && !d_maxs && !d_first) {
+    if (hash_empty && order != WDB_ORDER_FIRST && !d_first) {
       // the whole result sits in the direct-addressed table, already in key order: rank + emit, no sort
       wdb::DenseScratch sc;
       if (wdb::dense_rank(t, s, &sc)) return 1;
@@ -714,7 +772,7 @@ int wdb_agg_export(wdb_agg_t *t, void *stream, int agg, int order, int32_t *d_ke
       if ((long long)total > cap) { cudaFreeAsync(sc.buf, s); return fail("%lld groups exceed the output capacity %lld", (long long)total, (long long)cap); }
       if (total) {
         WDB_DENSE_DISPATCH(t->needs, (dense_emit_kernel<N><<<(unsigned)sc.ntiles, kDenseBlock, 0, s>>>(t->T, sc.tile_offsets, sc.total, order == WDB_ORDER_KEY_DESC, agg, 0,
-                                                                                                      d_keys, d_vals, d_sums, (long long *)d_counts)));
+                                                                                                      (long long)cap, d_keys, d_vals, d_sums, (long long *)d_counts, d_mins, d_maxs)));
         stats().launches++;
         WDB_CUDA(cudaGetLastError());
       }
@@ -757,7 +815,7 @@ int wdb_group_agg(int device, void *stream, const wdb_col_t *cols, int ncols, co
   int64_t expect = expected_groups > 0 ? expected_groups : 1 << 16;
   for (int attempt = 0; attempt < 6; ++attempt) {
     wdb_agg_t *t = nullptr;
-    if (wdb_agg_create(device, expect, needs, &t)) return 1;
+    if (wdb::agg_create_on(device, expect, needs, (cudaStream_t)stream, &t)) return 1;
     int rc = wdb_agg_consume(t, stream, cols, ncols, val_expr, key_expr, cond, n, 0);
     int64_t g = 0;
     if (!rc) rc = wdb_agg_export(t, stream, agg, order, d_keys, d_vals, nullptr, nullptr, nullptr, nullptr, nullptr, cap, &g);

@@ -18,6 +18,7 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
                    const char *cond, float *d_out, float *d_out2, int64_t n, int64_t *d_count, int64_t *h_count,
                    int thresh, float tau, int64_t out_cap, const unsigned char *zmask = nullptr, int zshift = 0);
 int sort_f32(Device *d, cudaStream_t s, float *d_keys, float *d_payload, long long n, bool ascending);
+std::string order_key(const char *key_expr, bool desc);
 
 struct TopkPlan { GenSpec spec; int block, unroll, vec, K; };
 
@@ -108,6 +109,55 @@ static int topk_small(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncol
   return 0;
 }
 
+// NaN keys order after every number, whatever the direction and the path (prelude.cuh: wdb_nanlast_*)
+std::string order_key(const char *key_expr, bool desc) { return std::string(desc ? "wdb_nanlast_d(" : "wdb_nanlast_a(") + key_expr + ")"; }
+
+// Local phase of a sharded ORDER BY ... LIMIT (ops_comm.cu): the K = k+offset best (key, row) pairs of
+// this shard and the SELECT value at each of them, written as [K keys f32 | K vals f32 | K rows i64]
+// at `cand` (this rank's slot of the all-gather buffer).  Rows are global ids (row_base + local row);
+// empty entries carry WDB_ROW_NONE.  Asynchronous on `s`.
+int topk_candidates(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncols, const char *key, const char *val, const char *cond,
+                    bool desc, int K, int64_t n, int64_t row_base, char *cand) {
+  TopkPlan p;
+  if (plan_topk(cols, ncols, key, val, cond, desc, K, true, &p)) return 1;
+  const std::string src = gen_source(p.spec);
+  Kernel scan, fin, emit;
+  if (get_kernel(d, src, "wdb_topk.cu", "wdb_topk_scan", &scan) || get_kernel(d, src, "wdb_topk.cu", "wdb_topk_final", &fin) ||
+      get_kernel(d, src, "wdb_topk.cu", "wdb_topk_emit", &emit))
+    return 1;
+  int nb = 0;
+  WDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)scan.fn, p.block, 0));
+  nb = std::max(1, std::min<int>(nb, (int)opt("topk.ctas_per_sm", 8)));
+  const int64_t tile_rows = (int64_t)p.block * p.unroll * p.vec;
+  const int64_t ntiles = std::max<int64_t>(1, (n + tile_rows - 1) / tile_rows);
+  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)d->num_sms * nb);
+  const size_t ncand = (size_t)grid * K;
+  char *buf = nullptr;
+  WDB_CUDA(cudaMallocAsync((void **)&buf, ncand * 12 + 64, s));
+  long long *cand_r = (long long *)buf;
+  long long *d_cnt = cand_r + ncand;
+  float *cand_k = (float *)(d_cnt + 2);
+  float *best_k = (float *)cand, *best_v = best_k + K, *no_keys = nullptr;
+  long long *best_r = (long long *)(cand + (size_t)K * 8);
+  auto ptrs = col_ptrs(p.spec, cols);
+  long long nn = n, rb = row_base, m = (long long)ncand;
+  int zero = 0;
+  {
+    void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r};
+    if (launch(scan, grid, p.block, 0, s, args)) return 1;
+  }
+  {
+    void *args[] = {&cand_k, &cand_r, &m, &best_k, &best_r};
+    if (launch(fin, 1, p.block, 0, s, args)) return 1;
+  }
+  {
+    void *args[] = {ptrs.data(), &rb, &best_k, &best_r, &zero, &best_v, &no_keys, &d_cnt};
+    if (launch(emit, 1, 32, 0, s, args)) return 1;
+  }
+  WDB_CUDA(cudaFreeAsync(buf, s));
+  return 0;
+}
+
 static int topk_large(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncols, const char *key, const char *val, const char *cond,
                       bool desc, int64_t k, int64_t offset, int64_t n, float *d_out_vals, float *d_out_keys, int64_t *h_n) {
   const bool limited = k >= 0;
@@ -178,6 +228,8 @@ extern "C" int wdb_topk(int device, void *stream, const wdb_col_t *cols, int nco
   Device *d;
   if (get_device(device, &d)) return 1;
   cudaStream_t s = (cudaStream_t)stream;
+  const std::string nan_last = order_key(key_expr, descending != 0);   // NaN keys order last in every path
+  key_expr = nan_last.c_str();
   if (k == 0) { if (h_n) *h_n = 0; return 0; }
   const int64_t reg_max = opt("topk.reg_max", 16);
   if (k > 0 && k + offset <= reg_max)

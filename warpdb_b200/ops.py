@@ -258,3 +258,102 @@ def project_filter_pruned(table, expr, cond, preds, mode=wc.DENSE_ZERO, out=None
     wc.check(wc.lib().wdb_project_filter_pruned(dev, _stream(dev), cols, nc, wc.enc(expr), wc.enc(cond), out.data_ptr(), n, mode, None,
                                                 C.byref(cnt) if sync else None, arr, len(preds), C.byref(live) if sync else None))
     return out, (cnt.value if sync else None), (live.value if sync else None)
+
+
+class Comm:
+    """One GPU's membership in a group of GPUs (wdb_comm_*): the handle the sharded operators of the
+    core (wdb_multi_*) take.  The cross-GPU merges run inside libwarpcore over NCCL/NVLink; Python only
+    carries the 128-byte NCCL id from rank 0 to the other ranks (torch.distributed, any backend)."""
+
+    def __init__(self, device=0, rank=0, world=1, unique_id=None):
+        self.device, self.rank, self.world = device, rank, world
+        self.handle = C.c_void_p()
+        buf = None
+        if world > 1:
+            if unique_id is None or len(unique_id) != 128:
+                raise wc.WarpcoreError("a communicator of several ranks needs the 128-byte id of Comm.unique_id()")
+            buf = C.create_string_buffer(bytes(unique_id), 128)
+        wc.check(wc.lib().wdb_comm_init_rank(device, world, rank, buf, C.byref(self.handle)))
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        wc.check(wc.lib().wdb_comm_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_torch(cls, device, group=None):
+        """One process per GPU under torch.distributed: rank 0 creates the id, broadcast carries it."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return cls(device, 0, 1)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if world == 1:
+            return cls(device, 0, 1)
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{device}" if on_gpu else "cpu")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls(device, rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    def close(self):
+        if self.handle:
+            wc.lib().wdb_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- sharded operators: `table` is this rank's shard -------------------------------------------
+    def project_filter(self, table, expr, cond=None, mode=wc.COMPACT, out=None, sync=True):
+        """Returns (out, (rows written, global offset, global total)) -- the triple is None when sync=False."""
+        n = num_rows(table)
+        if out is None:
+            out = torch.empty(max(n, 1), dtype=torch.float32, device=f"cuda:{self.device}")[:n]
+        cols, nc = wc.make_cols(schema_of(table))
+        h3 = (C.c_int64 * 3)()
+        wc.check(wc.lib().wdb_multi_project_filter(self.handle, _stream(self.device), cols, nc, wc.enc(expr), wc.enc(cond or ""), out.data_ptr(), n, mode,
+                                                   None, h3 if sync else None))
+        return out, (tuple(h3) if sync else None)
+
+    def group_agg(self, table, val_expr, key_expr, cond=None, agg=wc.SUM, order=wc.ORDER_KEY_ASC, row_base=0, expected_groups=0,
+                  key_range=None, cap=None, out=None, sync=True):
+        """Final groups of the whole sharded table on every rank: (keys int32[G], vals float32[G]).
+        out=(keys, vals, groups) reuses caller buffers; sync=False returns them unsliced with the group
+        count left on the device in groups[0]."""
+        n = num_rows(table)
+        dev = f"cuda:{self.device}"
+        if out is None:
+            if cap is None:
+                cap = max(2 * expected_groups + 16, 1 << 16) if expected_groups else 1 << 24
+                if key_range is not None:
+                    cap = min(cap, key_range[1] - key_range[0] + 1)
+            out = (torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.float32, device=dev),
+                   torch.zeros(1, dtype=torch.int64, device=dev))
+        keys, vals, groups = out
+        cols, nc = wc.make_cols(schema_of(table))
+        g = C.c_int64(0)
+        known = key_range is not None
+        wc.check(wc.lib().wdb_multi_group_agg(self.handle, _stream(self.device), cols, nc, wc.enc(val_expr), wc.enc(key_expr), wc.enc(cond or ""), agg, order,
+                                              n, row_base, expected_groups, int(known), int(key_range[0]) if known else 0, int(key_range[1]) if known else -1,
+                                              keys.data_ptr(), vals.data_ptr(), keys.numel(), groups.data_ptr(), C.byref(g) if sync else None))
+        if sync:
+            return keys[:g.value], vals[:g.value]
+        return keys, vals, groups
+
+    def topk(self, table, key_expr, val_expr=None, cond=None, descending=True, k=5, offset=0, row_base=0, out=None, sync=True):
+        """ORDER BY key [DESC] LIMIT k OFFSET offset over the whole sharded table; same values on every rank."""
+        n = num_rows(table)
+        dev = f"cuda:{self.device}"
+        if out is None:
+            out = (torch.empty(max(k, 1), dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.int64, device=dev))
+        vals, cnt = out
+        cols, nc = wc.make_cols(schema_of(table))
+        h = C.c_int64(0)
+        wc.check(wc.lib().wdb_multi_topk(self.handle, _stream(self.device), cols, nc, wc.enc(key_expr), wc.enc(val_expr), wc.enc(cond or ""), int(descending),
+                                         k, offset, n, row_base, vals.data_ptr(), None, cnt.data_ptr(), C.byref(h) if sync else None))
+        return vals[:h.value] if sync else vals

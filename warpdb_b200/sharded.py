@@ -21,6 +21,13 @@ over devices with host-mediated copies and no inter-GPU traffic at all) for resi
 The collectives are the only cross-rank data path; `backend` does the per-rank work (CUDA kernels
 through the C ABI by default; the CPU tests plug in a NumPy/oracle backend to exercise this file's
 logic under gloo).
+
+On GPUs the default strategy is "core": the merges run inside libwarpcore (wdb_multi_group_agg /
+wdb_multi_topk / wdb_multi_project_filter over its own NCCL communicator, include/warpcore.h) and this
+file is only a thin caller -- it carries the NCCL id to the other ranks and caches the global min/max
+of GROUP BY key columns (the optimizer statistics).  The torch.distributed strategies below
+("allgather", "exchange") remain as the reference implementation of the same merges; they are what
+the gloo tests exercise on the CPU.
 """
 import torch
 import torch.distributed as dist
@@ -98,8 +105,9 @@ class CudaBackend:
     def merge_partials(self, parts, needs, expected, agg, order):
         if len(parts) == 1 and order == wc.ORDER_KEY_ASC:
             # single GPU: the partial table is the result; re-export with the requested aggregate
-            tab = self._tables[("partial", expected, needs)]
-            return tab.export(agg, order, raw=True)
+            tab = getattr(self, "_tables", {}).get(("partial", expected, needs))
+            if tab is not None:
+                return tab.export(agg, order, raw=True)
         tab = self._table("merge", expected, needs)
         live = [p for p in parts if p["keys"].numel()]
         if live and (needs & ~(wc.NEED_SUM | wc.NEED_COUNT)) == 0:
@@ -143,6 +151,45 @@ class ShardedDB:
         dev = next(iter(table.values())).device if table else torch.device("cpu")
         self.device = dev
         self.backend = backend if backend is not None else CudaBackend(dev.index or 0)
+        self._comm = None
+        self._ranges = {}
+
+    # ---- core communicator (GPU only) ------------------------------------------------------------
+    def _core(self):
+        """The wdb_comm of this rank, or None when the per-rank work is not done by libwarpcore."""
+        if not isinstance(self.backend, CudaBackend):
+            return None
+        if self._comm is None:
+            from . import ops
+            if self.world == 1:
+                self._comm = ops.Comm(self.backend.device, 0, 1)
+            else:
+                self._comm = ops.Comm.from_torch(self.backend.device, self.group)
+        return self._comm
+
+    def _global_key_range(self, key):
+        """Global [min, max] of a bare int32 GROUP BY column: local min/max (one streaming pass) + one
+        all_reduce, cached per column tensor (and invalidated by in-place writes)."""
+        import re
+        from . import ops
+        m = re.fullmatch(r"\(?\s*([A-Za-z_]\w*)\[idx\]\s*\)?", key.strip())
+        col = self.table.get(m.group(1)) if m else None
+        if col is None or col.dtype != torch.int32:
+            return None
+        hit = self._ranges.get(m.group(1))
+        if hit is not None and hit[0] is col and hit[1] == col._version:
+            return hit[2]
+        big = float(1 << 40)
+        lo, hi = (big, -big)
+        if col.numel():
+            lo, hi = ops.column_minmax(col, m.group(1))
+        ends = torch.tensor([lo, -hi], dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(ends, op=dist.ReduceOp.MIN, group=self.group)
+        lo, hi = int(ends[0].item()), int(-ends[1].item())
+        rng = (lo, hi) if lo <= hi else None
+        self._ranges[m.group(1)] = (col, col._version, rng)
+        return rng
 
     # ---- collectives ---------------------------------------------------------------------------
     def _all_gather_var(self, t):
@@ -202,6 +249,10 @@ class ShardedDB:
 
     def query_compact(self, expr, cond):
         """Stable compaction: returns (local survivors, global offset of the first one, global count)."""
+        comm = self._core()
+        if comm is not None:
+            out, (cnt, off, total) = comm.project_filter(self.table, expr, cond, wc.COMPACT)
+            return out[:cnt], off, total
         out, cnt = self.backend.project_filter(self.table, expr, cond, wc.COMPACT)
         c = torch.tensor([cnt], dtype=torch.int64, device=self.device)
         if self.world > 1:
@@ -216,6 +267,11 @@ class ShardedDB:
         """GROUP BY over all shards.  Every rank returns the same dict(keys, vals, ...) of final groups."""
         from .ops import needs_for
         needs = needs_for(agg, order)
+        comm = self._core() if strategy in ("auto", "core") else None
+        if comm is not None:
+            rng = self._global_key_range(key)
+            keys, vals = comm.group_agg(self.table, val, key, cond, agg, order, row_base=self.row0, expected_groups=expected_groups, key_range=rng)
+            return {"keys": keys, "vals": vals}
         if self.world == 1 and hasattr(self.backend, "group_local"):
             return self.backend.group_local(self.table, val, key, cond, needs, expected_groups, agg, order)
         part = self.backend.group_partials(self.table, val, key, cond, needs, expected_groups, self.row0)
@@ -240,8 +296,8 @@ class ShardedDB:
             ends = torch.stack((keys[0].to(torch.int64), -keys[-1].to(torch.int64)))
         dist.all_reduce(ends, op=dist.ReduceOp.MIN, group=self.group)
         lo, hi = int(ends[0]), -int(ends[1])
-        if lo == big:                                   # no rank has any group
-            return self.backend.merge_partials([part], needs, 1024, agg, order)
+        if lo == big:                                   # no rank has any group: every partial is empty, and so is the result
+            return dict(part, vals=torch.empty(0, dtype=torch.float32, device=self.device))
         span = hi - lo + 1
         bounds = torch.tensor([lo + (span * r + self.world - 1) // self.world for r in range(1, self.world)], dtype=keys.dtype, device=self.device)
         cuts = [0] + torch.searchsorted(keys, bounds).tolist() + [keys.numel()]
@@ -269,10 +325,13 @@ class ShardedDB:
         idx = torch.argsort(allg["first"], stable=True)
         return {k: v[idx] for k, v in allg.items()}
 
-    def topk(self, key, val=None, cond=None, descending=True, k=5, offset=0):
+    def topk(self, key, val=None, cond=None, descending=True, k=5, offset=0, strategy="auto"):
         """ORDER BY key [DESC] LIMIT k OFFSET offset over all shards; same result on every rank."""
         if k < 0:
             raise ValueError("sharded ORDER BY needs a LIMIT")
+        comm = self._core() if strategy in ("auto", "core") else None
+        if comm is not None:
+            return comm.topk(self.table, key, val, cond, descending, k, offset, row_base=self.row0)
         vals, keys = self.backend.topk_local(self.table, key, val or key, cond, descending, k + offset)
         if self.world == 1:
             return vals[offset:offset + k]
