@@ -1,25 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the WarpDB hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workloads LIST]
 
 One "step" = one pass of the hot path over one batch of synthetic, HBM-resident columns.
-Default workload = BASELINE.json configs[1]: pure projection "price * quantity * 1.08" over
-1e9 rows (price float32, quantity int32; 12 algorithmic bytes per row) per GPU (weak scaling:
-row-range shards, no data-path collective).  Other workloads (--workload) are the remaining
-BASELINE configs; they are parity-test cases with a measurement, not the headline line.
 
-Prints ONE JSON line (rank 0).  `value` is rows/s over all GPUs with inputs resident in HBM;
-`e2e` is the same metric through the host-buffer entry point (H2D and D2H inside the timed region);
-`roofline` compares the dominant kernel with the measured HBM copy peak (MEASURED_PEAKS.json);
-`cpu_baseline` is the CPU oracle (scalar AST evaluation, all host threads) on a bounded sample;
-`ref_nvrtc` is the reference's own NVRTC kernel (oracle/_ref/libref_jit.so) on the same arrays.
+Headline (`value`, `roofline`, `e2e`): BASELINE.json configs[1], pure projection
+"price * quantity * 1.08" over 1e9 rows PER GPU (price float32, quantity int32; 12 algorithmic bytes
+per row); row-range shards, no data-path collective, weak scaling.
+
+`workloads`: the remaining BASELINE configs in the SAME JSON line, each at its BASELINE size for the
+whole job (shards of it for N > 1, i.e. strong scaling) with the cross-GPU merge INSIDE the step:
+    filter1 / filter50 / filter99   "price * 0.9 WHERE price > 20", stable compaction, 4e9 rows   (configs[2])
+    group1k / group10m              "SELECT SUM(price) FROM t GROUP BY quantity", 2e9 rows       (configs[3])
+    topk5                           "SELECT discount(price, 0.9) ... ORDER BY ... DESC LIMIT 5", 8e9 rows (configs[4])
+Every sub-record carries ms_per_step (CUDA events, max over ranks), rows/s of the whole job, the
+roofline of its dominant kernel, merge_ms (step minus the same step without collectives), the
+collectives used, clocks sampled during its timed region and a result check.
+
+Prints ONE JSON line (rank 0).  `e2e` is the projection through the host-buffer entry point
+(wdb_multi_project_filter_host: H2D and D2H inside the timed region); `cpu_baseline` is the CPU
+oracle on a bounded sample; `ref_nvrtc` is the reference's own NVRTC kernel
+(oracle/_ref/libref_jit.so) on the same arrays.
 """
 import argparse
 import ctypes as C
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -27,17 +34,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {
-    # name: (rows per GPU, description)
-    "projection": (1_000_000_000, "price * quantity * 1.08 over 1e9 rows/GPU (f32 price, i32 quantity): BASELINE configs[1]"),
-    "filter1": (1_000_000_000, "price * 0.9 WHERE price > 20, 1% selectivity, stable compaction: BASELINE configs[2] (per-GPU shard of 4e9/4)"),
-    "filter50": (1_000_000_000, "price * 0.9 WHERE price > 20, 50% selectivity, stable compaction"),
-    "filter99": (1_000_000_000, "price * 0.9 WHERE price > 20, 99% selectivity, stable compaction"),
-    "group1k": (1_000_000_000, "SELECT SUM(price) FROM t GROUP BY quantity, 1K keys: BASELINE configs[3] (per-GPU shard)"),
-    "group10m": (1_000_000_000, "SELECT SUM(price) FROM t GROUP BY quantity, 10M keys"),
-    "topk5": (2_000_000_000, "SELECT discount(price, 0.9) FROM t ORDER BY discount(price, 0.9) DESC LIMIT 5: BASELINE configs[4] (per-GPU shard)"),
-}
+ALL_WORKLOADS = ["filter1", "filter50", "filter99", "group1k", "group10m", "topk5"]
+TOTAL_ROWS = {"projection": None, "filter1": 4_000_000_000, "filter50": 4_000_000_000, "filter99": 4_000_000_000,
+              "group1k": 2_000_000_000, "group10m": 2_000_000_000, "topk5": 8_000_000_000}
+PROJECTION_ROWS_PER_GPU = 1_000_000_000
 UDF = "__device__ float discount(float price, float rate) {\n    return price * rate;\n}\n"
+SEED = 0xC0FFEE
 
 
 def metric_name():
@@ -55,55 +57,94 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_per_row(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per row of the committed `ncu --set full` capture
+    (profiles/traffic.json; measured once per kernel, scaled by rows here -- it is NOT measured in this run)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        k = t["kernels"].get(kernel)
+        return (k["dram_bytes_per_row"], t.get("source", "profiles/traffic.json")) if k else (None, None)
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons of one GPU, sampled in-process through NVML every ~2 ms while a
+    timed region is open (`with sampler.region(): ...`).  nvidia-smi -lms needs ~100 ms to produce
+    its first line, longer than a 30 ms timed region; NVML does not."""
+    BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
-
-    def start(self):
+    def __init__(self, torch_device_index):
+        self.ok = False
+        self.samples = []
+        self.on = False
+        self.stop_flag = False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:  # noqa: BLE001
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
             try:
-                sm.append(float(f[1]))
-                mx = float(f[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:  # noqa: BLE001
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_device_index)   # no CUDA_VISIBLE_DEVICES remapping: same order
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            if self.on:
+                try:
+                    mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    try:
+                        reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:  # noqa: BLE001
+                        reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.samples.append((float(mhz), int(reasons)))
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(0.001)
+            else:
+                time.sleep(0.0005)
+
+    class _Region:
+        def __init__(self, s):
+            self.s = s
+
+        def __enter__(self):
+            self.s.samples = []
+            self.s.on = True
+
+        def __exit__(self, *a):
+            self.s.on = False
+
+    def region(self):
+        return ClockSampler._Region(self)
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")], "samples": 0}
+        sm = sorted(m for m, _ in self.samples)
+        reasons = set()
+        for _, r in self.samples:
+            for name, bit in self.BAD.items():
+                if r & bit:
                     reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "NVML in-process, ~2 ms period, timed region only"}
+
+    def close(self):
+        self.stop_flag = True
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -135,149 +176,264 @@ def max_over_ranks(x, world):
     return float(t.item())
 
 
-# ------------------------------------------------------------------------------------------------
-# workloads: setup(rank, world, local) -> dict(step=callable, rows, bytes_per_row, kernel, ...)
-# ------------------------------------------------------------------------------------------------
-def make_workload(name, rows, rank, world, local):
+def time_steps(step, steps, warmup, world, sampler=None):
+    """W untimed steps, then exactly K steps between barrier + synchronize on both sides, CUDA events on
+    the launching stream, max over ranks.  Returns (total ms, launches of our kernels inside the timed region, clocks)."""
     import torch
-    from warpdb_b200 import _core as wc, ops
-    wc.check(wc.lib().wdb_init(local))
-    wc.set_udf_source(UDF)
-    row0 = rank * rows                       # contiguous row-range shard of the global table (multi_gpu_utils.cpp:24-31)
-    seed = 0xC0FFEE
-    if name == "projection":
-        price = ops.synth_f32(rows, seed + 2, 0.0, 100.0, row0, local)
-        qty = ops.synth_i32(rows, seed + 102, 1, 101, row0, local)
-        out = torch.empty(rows, dtype=torch.float32, device=f"cuda:{local}")
-        table = {"price": price, "quantity": qty}
-        expr = "((price[idx] * quantity[idx]) * 1.08f)"
-        return dict(step=lambda: ops.project_filter(table, expr, None, wc.DENSE, out=out, sync_count=False),
-                    bytes_per_row=12.0, kernel="wdb_project", table=table, expr=expr, cond=None, query="price * quantity * 1.08",
-                    check=lambda: bool(torch.equal(out[:1 << 20], ((price[:1 << 20] * qty[:1 << 20].float()) * 1.08))))
-    if name.startswith("filter"):
-        sel = {"filter1": 0.01, "filter50": 0.5, "filter99": 0.99}[name]
-        price = ops.synth_f32(rows, seed + 3, 0.0, 20.0 / (1.0 - sel), row0, local)
-        out = torch.empty(rows, dtype=torch.float32, device=f"cuda:{local}")
-        table = {"price": price}
-        expr, cond = "(price[idx] * 0.9f)", "(price[idx] > 20.0f)"
-        _, cnt = ops.project_filter(table, expr, cond, wc.COMPACT, out=out)
-        return dict(step=lambda: ops.project_filter(table, expr, cond, wc.COMPACT, out=out, sync_count=False),
-                    bytes_per_row=4.0 + 4.0 * cnt / rows, kernel="wdb_compact_l2", table=table, expr=expr, cond=cond,
-                    query="price * 0.9 WHERE price > 20", selectivity=cnt / rows,
-                    check=lambda: bool(torch.equal(out[:cnt][:1 << 20], (price[price > 20.0][:1 << 20] * 0.9))))
-    if name.startswith("group"):
-        from warpdb_b200.sharded import ShardedDB
-        G = 1000 if name == "group1k" else 10_000_000
-        price = ops.synth_f32(rows, seed + 4, 0.0, 100.0, row0, local)
-        qty = ops.synth_i32(rows, seed + 104, 0, G, row0, local)
-        table = {"price": price, "quantity": qty}
-        db = ShardedDB(table, rows * world, rank, world)
-        res = {}
-
-        def step():   # per-GPU partial aggregation + (N > 1) NCCL merge of the partials; every rank ends with the final groups
-            res["g"] = db.group_agg("price[idx]", "quantity[idx]", None, wc.SUM, wc.ORDER_KEY_ASC, expected_groups=G)
-
-        def check():
-            tot = price.double().sum()
-            if world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(tot)
-            g = res["g"]
-            return bool(g["keys"].numel() == G and abs(g["vals"].double().sum().item() / tot.item() - 1.0) < 1e-6)
-        def kernel_ms(reps=5):   # the dominant kernel alone (consume), CUDA events on the launching stream
-            tab = ops.AggTable(local, G, wc.NEED_SUM)
-            tab.set_key_range(0, G - 1)
-            best = []
-            for _ in range(reps + 1):
-                tab.reset()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); tab.consume(table, "price[idx]", "quantity[idx]"); e1.record(); torch.cuda.synchronize()
-                best.append(e0.elapsed_time(e1))
-            tab.close()
-            return sum(best[1:]) / reps
-        return dict(step=step, bytes_per_row=8.0, kernel="wdb_group_wp" if G <= 4096 else "wdb_group", table=table, kernel_ms=kernel_ms,
-                    query="SELECT SUM(price) FROM t GROUP BY quantity",
-                    groups=G, check=check)
-    if name == "topk5":
-        from warpdb_b200.sharded import ShardedDB
-        price = ops.synth_f32(rows, seed + 5, 0.0, 1e6, row0, local)
-        table = {"price": price}
-        db = ShardedDB(table, rows * world, rank, world)
-        res = {}
-
-        def step():   # per-GPU top-k + (N > 1) all_gather of k candidates per GPU and a final merge
-            res["top"] = db.topk("discount(price[idx], 0.9f)", None, None, True, 5)
-
-        def check():
-            loc = torch.topk(price * 0.9, 5).values
-            if world > 1:
-                import torch.distributed as dist
-                allc = [torch.empty_like(loc) for _ in range(world)]
-                dist.all_gather(allc, loc)
-                loc = torch.topk(torch.cat(allc), 5).values
-            return bool(torch.equal(res["top"], loc))
-        return dict(step=step, bytes_per_row=4.0, kernel="wdb_topk_scan", table=table,
-                    query="SELECT discount(price, 0.9) FROM t ORDER BY discount(price, 0.9) DESC LIMIT 5", check=check)
-    raise SystemExit(f"unknown workload {name}")
-
-
-def time_steps(step, steps, warmup, world):
-    import torch
+    from warpdb_b200 import _core as wc
     for _ in range(warmup):
         step()
     barrier(world)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = wc.stats()["launches"]
+    if sampler:
+        sampler.on = True
+        sampler.samples = []
     a.record()
     for _ in range(steps):
         step()
     b.record()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.on = False
+    launches = wc.stats()["launches"] - l0
+    clocks = sampler.summary() if sampler else None
     barrier(world)
-    return max_over_ranks(a.elapsed_time(b), world)
+    return max_over_ranks(a.elapsed_time(b), world), launches, clocks
 
 
-def e2e_projection(rows, steps, warmup, world, local):
+def roofline(kernel, bytes_per_row, rows, kernel_ms, peak, peak_src, note=None):
+    achieved = bytes_per_row * rows / (kernel_ms * 1e-3) / 1e9
+    tpr, tsrc = traffic_per_row(kernel)
+    r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+         "traffic": tpr * rows if tpr else None,
+         "traffic_source": (f"{tsrc}: {tpr:.3f} DRAM bytes per row x rows of this launch (ncu capture, not measured in this run)" if tpr else None),
+         "kernel": kernel, "kernel_ms": kernel_ms, "peak_source": peak_src, "frac_of_8TBs_spec": achieved / 8000.0,
+         "algorithmic_bytes_per_row": bytes_per_row, "algorithmic_bytes_per_launch": bytes_per_row * rows}
+    if note:
+        r["note"] = note
+    return r
+
+
+def shard_rows(total, world, rank):
+    chunk = (total + world - 1) // world
+    s = min(rank * chunk, total)
+    return s, min(s + chunk, total) - s
+
+
+# ------------------------------------------------------------------------------------------------
+# sub-workloads (BASELINE configs[2..4]); every function returns the record of its workload
+# ------------------------------------------------------------------------------------------------
+def run_filter(name, args, rank, world, local, comm, comm1, sampler, peak, peak_src):
+    import torch
+    from warpdb_b200 import _core as wc, ops
+    sel = {"filter1": 0.01, "filter50": 0.5, "filter99": 0.99}[name]
+    total = args.rows_total or TOTAL_ROWS[name]
+    row0, rows = shard_rows(total, world, rank)
+    price = ops.synth_f32(rows, SEED + 3, 0.0, 20.0 / (1.0 - sel), row0, local)
+    out = torch.empty(rows, dtype=torch.float32, device=f"cuda:{local}")
+    table = {"price": price}
+    expr, cond = "(price[idx] * 0.9f)", "(price[idx] > 20.0f)"
+    _, (cnt, off, tot) = comm.project_filter(table, expr, cond, wc.COMPACT, out=out)
+    ms, launches, clocks = time_steps(lambda: comm.project_filter(table, expr, cond, wc.COMPACT, out=out, sync=False), args.steps, args.warmup, world, sampler)
+    ms_local = ms
+    if world > 1:
+        ms_local, _, _ = time_steps(lambda: ops.project_filter(table, expr, cond, wc.COMPACT, out=out, sync_count=False), args.steps, args.warmup, world)
+    # result: survivor count and the first 2^20 survivors of this shard against torch; global offsets add up
+    m = min(rows, 1 << 24)
+    head = price[:m]
+    want = (head[head > 20.0] * 0.9)[:1 << 20]
+    ok = cnt == int((price > 20.0).sum().item()) and bool(torch.equal(out[:want.numel()], want))
+    if world > 1:
+        import torch.distributed as dist
+        c = torch.tensor([cnt, off], dtype=torch.int64, device="cuda")
+        allc = [torch.zeros_like(c) for _ in range(world)]
+        dist.all_gather(allc, c)
+        cs = [int(x[0]) for x in allc]
+        ok = ok and tot == sum(cs) and off == sum(cs[:rank])
+        okt = torch.tensor([int(ok)], device="cuda")
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        ok = bool(okt.item())
+    s = tot / total
+    bpr = 4.0 + 4.0 * cnt / max(rows, 1)
+    per = ms / args.steps
+    rec = {"query": "SELECT price * 0.9 FROM t WHERE price > 20 (stable compaction)", "baseline_config": "configs[2]", "selectivity": s,
+           "rows_total": total, "rows_per_gpu": rows, "scaling": "strong" if world > 1 else "n/a", "ms_per_step": per,
+           "value": total / (per * 1e-3), "unit": "rows/s",
+           "roofline": roofline("wdb_compact_l2", bpr, rows, ms_local / args.steps, peak, peak_src,
+                                "kernel_ms = the local compaction call (wdb_compact_l2 + its 1-CTA finish kernel) timed with CUDA events"),
+           "merge_ms": max(per - ms_local / args.steps, 0.0), "collectives": ["ncclAllGather(1 x int64 per rank: survivor counts)"] if world > 1 else [],
+           "gpu_launches": launches, "clocks": clocks, "result_checked": ok}
+    del price, out
+    return rec
+
+
+def run_group(name, args, rank, world, local, comm, comm1, sampler, peak, peak_src):
+    import torch
+    from warpdb_b200 import _core as wc, ops
+    G = 1000 if name == "group1k" else 10_000_000
+    total = args.rows_total or TOTAL_ROWS[name]
+    row0, rows = shard_rows(total, world, rank)
+    dev = f"cuda:{local}"
+    price = ops.synth_f32(rows, SEED + 4, 0.0, 100.0, row0, local)
+    qty = ops.synth_i32(rows, SEED + 104, 0, G, row0, local)
+    table = {"price": price, "quantity": qty}
+    # optimizer statistics of the key column (gathered once at load time, like WarpDB::query_sql caches them)
+    lo, hi = ops.column_minmax(qty, "quantity")
+    ends = torch.tensor([lo, -hi], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(ends, op=dist.ReduceOp.MIN)
+    rng = (int(ends[0].item()), int(-ends[1].item()))
+    bufs = (torch.empty(G + 16, dtype=torch.int32, device=dev), torch.empty(G + 16, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.int64, device=dev))
+
+    def step(c=comm):   # reset + local aggregation + NCCL all-reduce of the partial tables + ordered export; no host synchronisation
+        c.group_agg(table, "price[idx]", "quantity[idx]", None, wc.SUM, wc.ORDER_KEY_ASC, row_base=row0, expected_groups=G, key_range=rng, out=bufs, sync=False)
+    ms, launches, clocks = time_steps(step, args.steps, args.warmup, world, sampler)
+    keys, vals, groups = bufs
+    torch.cuda.synchronize()
+    g = int(groups.item())
+    got_vals = vals[:g].double().clone()
+    got_keys = keys[:g].clone()
+    ms_local = ms
+    if world > 1:
+        ms_local, _, _ = time_steps(lambda: step(comm1), args.steps, args.warmup, world)
+
+    # the dominant kernel alone (consume), CUDA events on the launching stream
+    tab = ops.AggTable(local, 1024, wc.NEED_SUM)
+    tab.set_key_range(*rng)
+    ts = []
+    for _ in range(6):
+        tab.reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); tab.consume(table, "price[idx]", "quantity[idx]"); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    tab.close()
+    kernel_ms = sum(ts[1:]) / (len(ts) - 1)
+    # result: every group's fp64 sum recomputed with torch (index_add_ in chunks), all-reduced; 1e-6 relative
+    ref = torch.zeros(G, dtype=torch.float64, device=dev)
+    step_rows = 1 << 27
+    for s in range(0, rows, step_rows):
+        ref.index_add_(0, qty[s:s + step_rows].long(), price[s:s + step_rows].double())
+    if world > 1:
+        dist.all_reduce(ref)
+    present = ref != 0
+    ok = g == int(present.sum().item()) and bool(torch.equal(got_keys.long(), torch.nonzero(present).flatten()))
+    if ok:
+        want = ref[present].float().double()
+        ok = bool(((got_vals - want).abs() <= 1e-6 * want.abs()).all().item())
+    per = ms / args.steps
+    kernel = "wdb_group_wp" if G <= 4096 else "wdb_group"
+    rec = {"query": "SELECT SUM(price) FROM t GROUP BY quantity", "baseline_config": "configs[3]", "groups": G,
+           "rows_total": total, "rows_per_gpu": rows, "scaling": "strong" if world > 1 else "n/a", "ms_per_step": per,
+           "value": total / (per * 1e-3), "unit": "rows/s",
+           "roofline": roofline(kernel, 8.0, rows, kernel_ms, peak, peak_src, "kernel_ms = the consume launch(es) alone; the step adds table reset, all-reduce and ordered export"),
+           "local_ms": ms_local / args.steps, "merge_ms": max(per - ms_local / args.steps, 0.0),
+           "collectives": [f"ncclAllReduce(sum, float64 x {rng[1] - rng[0] + 1}: direct-addressed partial sums)"] if world > 1 else [],
+           "merge_bytes_per_gpu": 8 * (rng[1] - rng[0] + 1) if world > 1 else 0,
+           "gpu_launches": launches, "clocks": clocks, "result_checked": ok}
+    del price, qty, ref
+    return rec
+
+
+def run_topk(name, args, rank, world, local, comm, comm1, sampler, peak, peak_src):
+    import torch
+    from warpdb_b200 import ops
+    total = args.rows_total or TOTAL_ROWS[name]
+    row0, rows = shard_rows(total, world, rank)
+    dev = f"cuda:{local}"
+    price = ops.synth_f32(rows, SEED + 5, 0.0, 1e6, row0, local)
+    table = {"price": price}
+    bufs = (torch.empty(5, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.int64, device=dev))
+
+    def step(c=comm):   # per-GPU register top-k + one all-gather of 5 candidates per GPU + one-warp selection; no host synchronisation
+        c.topk(table, "discount(price[idx], 0.9f)", None, None, True, 5, 0, row_base=row0, out=bufs, sync=False)
+    ms, launches, clocks = time_steps(step, args.steps, args.warmup, world, sampler)
+    torch.cuda.synchronize()
+    got = bufs[0].clone()
+    ms_local = ms
+    if world > 1:
+        ms_local, _, _ = time_steps(lambda: step(comm1), args.steps, args.warmup, world)
+    loc = torch.zeros(5, dtype=torch.float32, device=dev)
+    step_rows = 1 << 28
+    cands = [torch.topk(price[s:s + step_rows] * 0.9, min(5, price[s:s + step_rows].numel())).values for s in range(0, rows, step_rows)]
+    loc = torch.topk(torch.cat(cands), 5).values
+    if world > 1:
+        import torch.distributed as dist
+        allc = [torch.empty_like(loc) for _ in range(world)]
+        dist.all_gather(allc, loc)
+        loc = torch.topk(torch.cat(allc), 5).values
+    ok = int(bufs[1].item()) == 5 and bool(torch.equal(got, loc))
+    per = ms / args.steps
+    rec = {"query": "SELECT discount(price, 0.9) FROM t ORDER BY discount(price, 0.9) DESC LIMIT 5 (custom.cu UDF)", "baseline_config": "configs[4]",
+           "rows_total": total, "rows_per_gpu": rows, "scaling": "strong" if world > 1 else "n/a", "ms_per_step": per,
+           "value": total / (per * 1e-3), "unit": "rows/s",
+           "roofline": roofline("wdb_topk_scan", 4.0, rows, ms_local / args.steps, peak, peak_src,
+                                "kernel_ms = the local step (wdb_topk_scan + the 1-CTA final and emit kernels, ~15 us) timed with CUDA events"),
+           "merge_ms": max(per - ms_local / args.steps, 0.0),
+           "collectives": ["ncclAllGather(80 B per rank: 5 x (key f32, value f32, global row i64))"] if world > 1 else [],
+           "gpu_launches": launches, "clocks": clocks, "result_checked": ok}
+    del price
+    return rec
+
+
+RUNNERS = {"filter1": run_filter, "filter50": run_filter, "filter99": run_filter, "group1k": run_group, "group10m": run_group, "topk5": run_topk}
+
+
+# ------------------------------------------------------------------------------------------------
+# headline: projection, e2e, baselines
+# ------------------------------------------------------------------------------------------------
+def e2e_projection(rows, steps, warmup, world, rank, local):
     """Same metric through the host-buffer entry point (wdb_multi_project_filter_host: the
-    run_multi_gpu_jit_host replacement): pinned host columns in, host floats out, every step."""
+    run_multi_gpu_jit_host replacement): pinned host columns in, host floats out, every step.  ONE
+    process (rank 0) drives all N GPUs with one call, the shape of the reference's function; the
+    other ranks have released their GPU memory and wait."""
     import torch
     from warpdb_b200 import _core as wc
     from warpdb_b200 import ops
-    n = rows
-    # synthesise on the device once, keep pinned host copies as "the user's data"
-    hp = torch.empty(n, dtype=torch.float32, pin_memory=True)
-    hq = torch.empty(n, dtype=torch.int32, pin_memory=True)
-    ho = torch.empty(n, dtype=torch.float32, pin_memory=True)
-    chunk = 1 << 27
-    for s in range(0, n, chunk):
-        m = min(chunk, n - s)
-        hp[s:s + m].copy_(ops.synth_f32(m, 0xC0FFEE + 2, 0.0, 100.0, s, local))
-        hq[s:s + m].copy_(ops.synth_i32(m, 0xC0FFEE + 102, 1, 101, s, local))
-    torch.cuda.synchronize()
-    cols, nc = wc.make_cols([("price", wc.FLOAT32, hp.data_ptr(), n), ("quantity", wc.INT32, hq.data_ptr(), n)])
-    cnt = C.c_int64(0)
-    devs = (C.c_int * 1)(local)
+    torch.cuda.empty_cache()
+    barrier(world)
+    res = None
+    if rank == 0:
+        n = rows * world
+        hp = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        hq = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        ho = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        chunk = 1 << 27
+        for s in range(0, n, chunk):   # synthesise on the device once, keep pinned host copies as "the user's data"
+            m = min(chunk, n - s)
+            hp[s:s + m].copy_(ops.synth_f32(m, SEED + 2, 0.0, 100.0, s, local))
+            hq[s:s + m].copy_(ops.synth_i32(m, SEED + 102, 1, 101, s, local))
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        cols, nc = wc.make_cols([("price", wc.FLOAT32, hp.data_ptr(), n), ("quantity", wc.INT32, hq.data_ptr(), n)])
+        cnt = C.c_int64(0)
 
-    def step():
-        wc.check(wc.lib().wdb_multi_project_filter_host(1, devs, cols, nc, b"((price[idx] * quantity[idx]) * 1.08f)", b"",
-                                                        ho.data_ptr(), n, wc.DENSE_ZERO, C.byref(cnt)))
-    for _ in range(warmup):
-        step()
+        def step():
+            wc.check(wc.lib().wdb_multi_project_filter_host(world, None, cols, nc, b"((price[idx] * quantity[idx]) * 1.08f)", b"",
+                                                            ho.data_ptr(), n, wc.DENSE_ZERO, C.byref(cnt)))
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = time.perf_counter() - t0
+        idx = torch.randint(0, n, (1 << 20,))
+        ok = bool(torch.equal(ho[idx], (hp[idx] * hq[idx].float()) * 1.08)) and bool(torch.equal(ho[-(1 << 16):], (hp[-(1 << 16):] * hq[-(1 << 16):].float()) * 1.08))
+        res = dict(value=n * steps / dt, unit="rows/s", h2d_bytes_per_step=8 * n, d2h_bytes_per_step=4 * n,
+                   steps=steps, ms_per_step=dt / steps * 1e3, result_checked=ok, pcie_gbs=12.0 * n * steps / dt / 1e9,
+                   api=f"one call of wdb_multi_project_filter_host(ndev={world}) per step from ONE process (run_multi_gpu_jit_host replacement), pinned host buffers, "
+                       "wall clock around the calls (the call returns when the results are on the host)")
+        del hp, hq, ho
     barrier(world)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    barrier(world)
-    dt = max_over_ranks(time.perf_counter() - t0, world)
-    ok = bool(torch.equal(ho[:1 << 20], (hp[:1 << 20] * hq[:1 << 20].float()) * 1.08))
-    return dict(value=world * n * steps / dt, unit="rows/s", h2d_bytes_per_step=8 * n, d2h_bytes_per_step=4 * n,
-                steps=steps, ms_per_step=dt / steps * 1e3, result_checked=ok,
-                api="wdb_multi_project_filter_host (run_multi_gpu_jit_host replacement), pinned host buffers")
+    return res
 
 
 def cpu_baseline_projection(sample_rows, steps=1):
     """Scalar AST evaluation on the host cores (oracle port of src/warpdb.cpp:128-151 semantics)."""
     from oracle import pyoracle as orc
     cores = os.cpu_count() or 1
-    table = {"price": orc.synth_f32(sample_rows, 0xC0FFEE + 2, 0.0, 100.0), "quantity": orc.synth_i32(sample_rows, 0xC0FFEE + 102, 1, 101)}
+    table = {"price": orc.synth_f32(sample_rows, SEED + 2, 0.0, 100.0), "quantity": orc.synth_i32(sample_rows, SEED + 102, 1, 101)}
     best = None
     for _ in range(steps):
         t0 = time.perf_counter()
@@ -326,66 +482,65 @@ def ref_nvrtc_projection(table, rows, local):
 
 def run_ours(args):
     import torch
-    rank, world, local = dist_setup(args.gpus)
-    from warpdb_b200 import _core as wc
-    rows = args.rows or WORKLOADS[args.workload][0]
-    w = make_workload(args.workload, rows, rank, world, local)
+    rank, world, local = dist_setup()
+    from warpdb_b200 import _core as wc, ops
+    wc.check(wc.lib().wdb_init(local))
+    wc.set_udf_source(UDF)
     peak, peak_src = measured_peak()
-    sampler = ClockSampler(local)
-    # untimed: compile + warm
-    s0 = wc.stats()
-    w["step"]()
+    sampler = ClockSampler(local) if rank == 0 else None
+    rows = args.rows or PROJECTION_ROWS_PER_GPU
+    row0 = rank * rows                       # contiguous row-range shard of the global table (multi_gpu_utils.cpp:24-31)
+    price = ops.synth_f32(rows, SEED + 2, 0.0, 100.0, row0, local)
+    qty = ops.synth_i32(rows, SEED + 102, 1, 101, row0, local)
+    out = torch.empty(rows, dtype=torch.float32, device=f"cuda:{local}")
+    table = {"price": price, "quantity": qty}
+    expr = "((price[idx] * quantity[idx]) * 1.08f)"
+    step = lambda: ops.project_filter(table, expr, None, wc.DENSE, out=out, sync_count=False)  # noqa: E731
+    step()
     torch.cuda.synchronize()
     compile_ms = wc.stats()["last_compile_ms"]
-    l0 = wc.stats()["launches"]
-    if rank == 0:
-        sampler.start()
-    ms = time_steps(w["step"], args.steps, args.warmup, world)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = wc.stats()["launches"] - l0 - 0
-    launches_timed = launches * args.steps // (args.steps + args.warmup) if (args.steps + args.warmup) else 0
-    ok = w["check"]()
-    value = world * rows * args.steps / (ms * 1e-3)
+    ms, launches, clocks = time_steps(step, args.steps, args.warmup, world, sampler)
+    ok = bool(torch.equal(out[:1 << 20], ((price[:1 << 20] * qty[:1 << 20].float()) * 1.08))) and \
+        bool(torch.equal(out[-(1 << 20):], ((price[-(1 << 20):] * qty[-(1 << 20):].float()) * 1.08)))
     ms_per_step = ms / args.steps
-    # roofline: the dominant kernel's own launch time where a step launches more than one kernel
-    # (GROUP BY: consume vs reset / export / merge), else the step time
-    kernel_ms = w["kernel_ms"]() if "kernel_ms" in w else ms_per_step
-    achieved = w["bytes_per_row"] * rows / (kernel_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
-    # (profiles/traffic.json holds bytes per row measured on 2^28-row columns; scaled to this launch)
-    traffic = None
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"].get(w["kernel"])
-        if t and args.workload in ("projection", "topk5", "group1k", "filter50"):   # the captures were taken on these configurations
-            traffic = t["dram_bytes_per_row"] * rows
-    except Exception:  # noqa: BLE001
-        pass
     line = {
-        "metric": metric_name(), "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+        "metric": metric_name(), "value": world * rows / (ms_per_step * 1e-3), "unit": "rows/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (counter-based generator, identical on the CPU oracle)",
-        "config": {"workload": args.workload, "query": w["query"], "description": WORKLOADS[args.workload][1], "rows_per_gpu": rows,
-                   "sharding": "contiguous row ranges, one process per GPU, no data-path collective" if args.workload in ("projection",) or args.workload.startswith("filter") else "contiguous row ranges, one process per GPU; partial aggregates / top-k candidates merged with NCCL inside the step",
+        "config": {"workload": "projection", "query": "price * quantity * 1.08",
+                   "description": "price * quantity * 1.08 over 1e9 rows/GPU (f32 price, i32 quantity): BASELINE configs[1]; configs[2..4] are under `workloads`",
+                   "rows_per_gpu": rows, "sharding": "contiguous row ranges, one process per GPU, no data-path collective",
                    "l2": "inputs (>= 4 GB per column) are far larger than the 126 MB L2; no flush needed",
-                   "algorithmic_bytes_per_row": w["bytes_per_row"], "result_checked": ok},
-        "gbs_per_gpu": achieved,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": w["kernel"], "peak_source": peak_src, "frac_of_8TBs_spec": achieved / 8000.0,
-                     "algorithmic_bytes_per_launch": w["bytes_per_row"] * rows, "kernel_ms": kernel_ms},
-        "gpu_launches": launches_timed, "clocks": clocks, "nvrtc_compile_ms_untimed": compile_ms,
+                   "algorithmic_bytes_per_row": 12.0, "result_checked": ok},
+        "roofline": roofline("wdb_project", 12.0, rows, ms_per_step, peak, peak_src),
+        "gpu_launches": launches, "clocks": clocks, "nvrtc_compile_ms_untimed": compile_ms,
     }
-    for k in ("selectivity", "groups"):
-        if k in w:
-            line["config"][k] = w[k]
-    if args.workload == "projection":
-        if not args.no_e2e:
-            del w["step"]
-            line["e2e"] = e2e_projection(rows, max(1, min(args.steps, args.e2e_steps)), 1, world, local)
-        if rank == 0 and world == 1:
-            if not args.no_ref:
-                line["ref_nvrtc"] = ref_nvrtc_projection(w["table"], rows, local)
-            if not args.no_cpu:
-                line["cpu_baseline"] = cpu_baseline_projection(args.cpu_rows)
+    line["gbs_per_gpu"] = line["roofline"]["achieved"]
+    if rank == 0 and world == 1 and not args.no_ref:
+        line["ref_nvrtc"] = ref_nvrtc_projection(table, rows, local)
+    del price, qty, out, table, step
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, merges inside the step --------------------------------------
+    names = [w for w in (args.workloads.split(",") if args.workloads else []) if w]
+    if names:
+        comm = ops.Comm.from_torch(local)       # libwarpcore's own NCCL communicator (one rank per GPU)
+        comm1 = ops.Comm(local, 0, 1)           # the same entry points without collectives: local_ms / merge_ms
+        recs = {}
+        for w in names:
+            recs[w] = RUNNERS[w](w, args, rank, world, local, comm, comm1, sampler, peak, peak_src)
+            torch.cuda.empty_cache()
+        line["workloads"] = recs
+        comm.close()
+        comm1.close()
+    if not args.no_e2e:
+        e = e2e_projection(rows, max(1, min(args.steps, args.e2e_steps)), 1, world, rank, local)
+        if e:
+            line["e2e"] = e
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline_projection(args.cpu_rows)
+    if sampler:
+        sampler.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -404,7 +559,7 @@ def run_reference(args):
     from oracle import pyoracle as orc
     cores = os.cpu_count() or 1
     sample = args.cpu_rows
-    table = {"price": orc.synth_f32(sample, 0xC0FFEE + 2, 0.0, 100.0), "quantity": orc.synth_i32(sample, 0xC0FFEE + 102, 1, 101)}
+    table = {"price": orc.synth_f32(sample, SEED + 2, 0.0, 100.0), "quantity": orc.synth_i32(sample, SEED + 102, 1, 101)}
     for _ in range(args.warmup if args.warmup < 2 else 1):
         orc.project_filter("price * quantity * 1.08", None, table, nthreads=cores)
     t0 = time.perf_counter()
@@ -418,7 +573,8 @@ def run_reference(args):
         "impl": "reference", "metric": metric_name(), "value": value, "unit": "rows/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (counter-based generator)",
-        "config": {"workload": "projection", "query": "price * quantity * 1.08", "description": WORKLOADS["projection"][1],
+        "config": {"workload": "projection", "query": "price * quantity * 1.08",
+                   "description": "price * quantity * 1.08 over 1e9 rows/GPU (f32 price, i32 quantity): BASELINE configs[1]",
                    "rows_per_step": sample},
         "cpu_baseline": cb, "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
@@ -426,11 +582,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="projection", choices=sorted(WORKLOADS))
-    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: the workload's)")
+    ap.add_argument("--workloads", default=",".join(ALL_WORKLOADS), help="comma separated subset of " + ",".join(ALL_WORKLOADS) + " ('' = headline only)")
+    ap.add_argument("--rows", type=int, default=0, help="projection rows per GPU (default 1e9)")
+    ap.add_argument("--rows-total", type=int, default=0, help="override the total rows of every sub-workload (tests)")
     ap.add_argument("--cpu-rows", type=int, default=1 << 28, help="bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")

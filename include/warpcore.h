@@ -149,6 +149,13 @@ int wdb_column_minmax(int device, void *stream, const wdb_col_t *col, double *h_
  * the column is compared with a float literal (integers converted to float). */
 typedef struct wdb_zonemap wdb_zonemap_t;
 int wdb_zonemap_build(int device, void *stream, const wdb_col_t *col, int64_t zone_rows, wdb_zonemap_t **out);
+/* Resident ingest (upload_to_gpu, src/csv_loader.cpp:126-161: one synchronous pageable cudaMemcpy per
+ * column, no statistics): host column (h_col->dptr is a HOST pointer) -> d_dst in 64 MB chunks, pinned
+ * sources copied asynchronously, pageable ones through a pinned two-slot ring; the zone map
+ * (zone_rows as above; < 0 or out_zm == NULL: none) is filled on the device chunk by chunk while the
+ * next chunk is on the wire, and the exact column min/max (TableStats) is returned when asked for. */
+int wdb_upload_column(int device, void *stream, const wdb_col_t *h_col, void *d_dst, int64_t zone_rows, wdb_zonemap_t **out_zm,
+                      double *h_min, double *h_max);
 int wdb_zonemap_destroy(wdb_zonemap_t *z);
 int wdb_zonemap_info(const wdb_zonemap_t *z, int64_t *zone_rows, int64_t *nzones);
 /* one `column <op> constant` term of a conjunction; op: 0 '>' 1 '>=' 2 '<' 3 '<=' 4 '==' 5 '!=' */

@@ -166,7 +166,7 @@ def test_kernel_variants_agree(variant, vec, unroll, block):
             wc.set_option(k, None)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_compaction_variants_agree(variant):
     """ticket + register loads / TMA bulk ring / two-pass count-scan-scatter / L2-parked slabs: identical packed output."""
     n = 2_000_003
@@ -201,7 +201,7 @@ def test_kernel_cache_hits():
     assert s1["launches"] > s0["launches"]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("n", [1, 1023, 8192, 8193, 40_001, 1_000_001])
 def test_no_writes_outside_the_output(variant, n):
     """compute-sanitizer is closed on this pool: guard regions around the output buffer instead.  The

@@ -3,6 +3,8 @@
 // column count": src/csv_loader.cpp:49-68).
 #include "csv_loader.hpp"
 
+#include "warpcore.h"
+
 #include <cuda_runtime.h>
 
 #include <fstream>
@@ -138,18 +140,32 @@ HostTable load_csv_chunk(std::istream &stream, int max_rows, bool &finished, con
   return t;
 }
 
-Table upload_to_gpu(const HostTable &host) {
+Table upload_to_gpu(const HostTable &host) { return upload_to_gpu(host, nullptr); }
+
+Table upload_to_gpu(const HostTable &host, std::vector<ColumnIngestStats> *stats) {
   Table table;
   table.num_rows = host.num_rows();
   for (const auto &hc : host.columns) {
     void *d = nullptr;
     const size_t bytes = element_size(hc.type) * static_cast<size_t>(table.num_rows);
+    ColumnIngestStats st;
+    st.name = hc.name;
     if (hc.type != DataType::String) {   // string columns stay on the host (src/csv_loader.cpp:151-155)
       cuda_or_throw(cudaMalloc(&d, bytes ? bytes : 4), "cudaMalloc column");
-      if (bytes) cuda_or_throw(cudaMemcpy(d, host_data(hc), bytes, cudaMemcpyHostToDevice), "upload column");
+      const wdb_col_t col{hc.name.c_str(), static_cast<int>(hc.type), host_data(hc), table.num_rows};
+      wdb_zonemap_t *zm = nullptr;
+      const bool want = stats != nullptr && table.num_rows > 0;
+      if (wdb_upload_column(0, nullptr, &col, d, want ? 0 : -1, want ? &zm : nullptr, want ? &st.min : nullptr, want ? &st.max : nullptr)) {
+        cudaFree(d);
+        throw std::runtime_error(wdb_last_error());
+      }
+      st.numeric = want;
+      st.zonemap = zm;
     }
+    if (stats) stats->push_back(st);
     table.columns.push_back(ColumnDesc{hc.name, hc.type, d, table.num_rows});
   }
+  cuda_or_throw(cudaStreamSynchronize(nullptr), "upload");
   return table;
 }
 

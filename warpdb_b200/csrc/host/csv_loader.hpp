@@ -53,8 +53,21 @@ struct HostTable {
   std::vector<int> quantity;
 };
 
+// What the ingest pass learns about a column while it uploads it (the statistics the reference's
+// TableStats were meant to hold, per column instead of hard-wired to price / quantity): the exact
+// min / max and the zone map (an opaque wdb_zonemap_t*, owned by whoever receives this struct).
+struct ColumnIngestStats {
+  std::string name;
+  bool numeric = false;
+  double min = 0.0, max = 0.0;
+  void *zonemap = nullptr;
+};
+
 HostTable load_csv_to_host(const std::string &filepath, const std::vector<DataType> &schema = {});
+// src/csv_loader.cpp:126-161.  Columns go up in pinned, asynchronous chunks; with `stats` the zone map
+// and min / max of every numeric column are built on the device in the same pass (wdb_upload_column).
 Table upload_to_gpu(const HostTable &table);
+Table upload_to_gpu(const HostTable &table, std::vector<ColumnIngestStats> *stats);
 Table load_csv_to_gpu(const std::string &filepath, const std::vector<DataType> &schema = {});
 // At most max_rows rows from an open stream whose header line has already been consumed by the
 // caller.  `names` are the column names of that header (the reference re-reads a "header" from

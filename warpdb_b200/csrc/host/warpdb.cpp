@@ -200,16 +200,25 @@ WarpDB::WarpDB(const std::string &filepath, const std::vector<DataType> &schema)
   const auto dot = filepath.find_last_of('.');
   std::string ext = dot == std::string::npos ? "" : filepath.substr(dot + 1);
   for (auto &c : ext) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
+  // resident ingest: every numeric column's zone map and min / max are built on the device while the
+  // column is uploaded; queries find them ready instead of paying a pass on first use
+  std::vector<ColumnIngestStats> stats;
   if (ext == "csv") {
     host_table_ = load_csv_to_host(filepath, schema);
-    table_ = upload_to_gpu(host_table_);
+    table_ = upload_to_gpu(host_table_, &stats);
   } else if (ext == "json") {
     host_table_ = load_json_to_host(filepath);
-    table_ = upload_to_gpu(host_table_);
+    table_ = upload_to_gpu(host_table_, &stats);
   } else if (ext == "parquet" || ext == "arrow" || ext == "feather" || ext == "orc") {
     throw std::runtime_error("Arrow support is not compiled into WarpDB");   // src/warpdb.cpp:181-184
   } else {
     throw std::runtime_error("Unsupported file format: " + filepath);
+  }
+  for (size_t i = 0; i < stats.size() && i < table_.columns.size(); ++i) {
+    if (!stats[i].numeric) continue;
+    zonemaps_[stats[i].name] = stats[i].zonemap;
+    if (table_.columns[i].type == DataType::Int32)
+      key_ranges_[stats[i].name] = std::make_pair(static_cast<long long>(stats[i].min), static_cast<long long>(stats[i].max));
   }
 }
 

@@ -766,4 +766,132 @@ wdb_compact_l2(const wdb_cols C, float *__restrict__ out, float *__restrict__ ou
     }
   }
 }
+
+// ---- variant 4: ONE read, software-pipelined look-back (wdb_compact_sp) -------------------------
+// Variant 3 reads every slab twice (HBM, then L2) and pays three block barriers and a look-back on the
+// critical path of every slab; ncu shows it issue- and barrier-bound, not bandwidth-bound.  Here a
+// chunk's survivors are evaluated, ranked and staged in shared memory in the SAME pass that loads
+// them, and nothing waits for the global offset: WDB_NWARPS worker warps keep streaming chunks
+// while one extra warp (the scanner) does nothing but turn the workers' counts of round r into
+// global offsets (publish aggregate, decoupled look-back, publish prefix).  A worker copies the
+// staged survivors of round r - (S - 1) out after it has staged round r (S = WDB_SP_STAGES staging
+// buffers per warp), so the look-back of a round has S - 1 rounds of loads to hide behind.
+// Workers and scanner meet only through named barriers in the producer / consumer pattern of the
+// PTX ISA (barrier.arrive on one side, barrier.sync on the other): no __syncthreads, no ticket.
+// Slabs (one chunk per worker warp) are assigned round-robin, slab = round * gridDim.x + blockIdx.x,
+// which is deadlock-free because the grid never exceeds what is co-resident (host: occupancy).
+#ifndef WDB_SP_STAGES
+#define WDB_SP_STAGES 2
+#endif
+#define WDB_SP_THREADS (WDB_BLOCK + 32)
+__device__ __forceinline__ void wdb_bar_arrive(const int id) { asm volatile("barrier.arrive %0, %1;" :: "r"(id), "n"(WDB_SP_THREADS) : "memory"); }
+__device__ __forceinline__ void wdb_bar_sync(const int id) { asm volatile("barrier.sync %0, %1;" :: "r"(id), "n"(WDB_SP_THREADS) : "memory"); }
+#define WDB_SP_BAR_CNT(b) (1 + (b))
+#define WDB_SP_BAR_BASE(b) (1 + WDB_SP_STAGES + (b))
+
+extern __shared__ __align__(16) unsigned char wdb_sp_smem[];
+// layout: goff i64[S][NW] | wcount u32[S][NW] | stage f32[S][NW][WARP_ROWS] (| stage2 ...)
+#define WDB_SP_GOFF(b, w) (reinterpret_cast<i64 *>(wdb_sp_smem)[(b) * WDB_NWARPS + (w)])
+#define WDB_SP_WCNT(b, w) (reinterpret_cast<u32 *>(wdb_sp_smem + 8 * WDB_SP_STAGES * WDB_NWARPS)[(b) * WDB_NWARPS + (w)])
+#define WDB_SP_HDR ((12 * WDB_SP_STAGES * WDB_NWARPS + 15) / 16 * 16)
+#define WDB_SP_STAGE(b, w) (reinterpret_cast<float *>(wdb_sp_smem + WDB_SP_HDR) + ((size_t)(b) * WDB_NWARPS + (w)) * WDB_WARP_ROWS)
+#define WDB_SP_STAGE2(b, w) (WDB_SP_STAGE(b, w) + (size_t)WDB_SP_STAGES * WDB_NWARPS * WDB_WARP_ROWS)
+
+__device__ __forceinline__ void wdb_sp_copy_out(const int b, const u32 warp, const u32 lane, float *__restrict__ out, float *__restrict__ out2, const i64 out_cap) {
+  const i64 g0 = WDB_SP_GOFF(b, warp);
+  const int total = (int)WDB_SP_WCNT(b, warp);
+  const float *st = WDB_SP_STAGE(b, warp);
+#if WDB_NOUT == 2
+  const float *st2 = WDB_SP_STAGE2(b, warp);
+#endif
+  const int mis = (int)(g0 & 31);             // every store instruction of the loop covers one aligned 128-byte line
+  for (int i = (int)lane - mis; i < total; i += 32)
+    if (i >= 0 && g0 + i < out_cap) {
+      out[g0 + i] = st[i];
+#if WDB_NOUT == 2
+      out2[g0 + i] = st2[i];
+#endif
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(WDB_SP_THREADS, WDB_MIN_CTAS)
+wdb_compact_sp(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n, u64 *__restrict__ status,
+               i64 *__restrict__ out_count, const i64 nslabs, const i64 nchunks, const float wdb_tau, const i64 out_cap) {
+  const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const i64 first = blockIdx.x;
+  const i64 nr = first < nslabs ? (nslabs - first + gridDim.x - 1) / gridDim.x : 0;   // rounds of this CTA
+  if (warp == WDB_NWARPS) {
+    // ---- scanner warp: counts of round r -> global offsets of round r
+    for (i64 r = 0; r < nr; ++r) {
+      const int b = (int)(r % WDB_SP_STAGES);
+      const i64 slab = first + r * gridDim.x;
+      wdb_bar_sync(WDB_SP_BAR_CNT(b));
+      const u32 c = lane < WDB_NWARPS ? WDB_SP_WCNT(b, lane) : 0u;
+      u32 pre, ttotal;
+      wdb_warp_rank(c, lane, pre, ttotal);
+      i64 excl = 0;
+      if (slab == 0) {
+        if (lane == 0) wdb_st_status(&status[0], (WDB_ST_PREFIX << 62) | (u64)ttotal);
+      } else {
+        if (lane == 0) wdb_st_status(&status[slab], (WDB_ST_AGG << 62) | (u64)ttotal);
+        excl = wdb_lookback(status, slab, lane);
+        if (lane == 0) wdb_st_status(&status[slab], (WDB_ST_PREFIX << 62) | (u64)(excl + (i64)ttotal));
+      }
+      if (lane < WDB_NWARPS) WDB_SP_GOFF(b, lane) = excl + (i64)pre;
+      if (lane == 0 && slab == nslabs - 1) *out_count = excl + (i64)ttotal;
+      __syncwarp();
+      wdb_bar_arrive(WDB_SP_BAR_BASE(b));
+    }
+    return;
+  }
+  // ---- worker warps
+  for (i64 r = 0; r < nr; ++r) {
+    const int b = (int)(r % WDB_SP_STAGES);
+    const i64 chunk = (first + r * gridDim.x) * WDB_NWARPS + warp;
+    u32 total = 0;
+    if (chunk < nchunks) {
+      u32 flags[WDB_UNROLL];
+      float vals[WDB_UNROLL][WDB_VEC];
+#if WDB_NOUT == 2
+      float vals2[WDB_UNROLL][WDB_VEC];
+      wdb_chunk_flags<WDB_LD_HINT>(C, n, chunk, lane, wdb_tau, flags, vals, vals2, true);
+      float *st2 = WDB_SP_STAGE2(b, warp);
+#else
+      wdb_chunk_flags<WDB_LD_HINT>(C, n, chunk, lane, wdb_tau, flags, vals, true);
+#endif
+      float *st = WDB_SP_STAGE(b, warp);
+#pragma unroll
+      for (int u = 0; u < WDB_UNROLL; ++u) {
+        u32 pre, tot;
+        wdb_warp_rank(__popc(flags[u]), lane, pre, tot);
+        u32 pos = total + pre;
+#pragma unroll
+        for (int j = 0; j < WDB_VEC; ++j)
+          if ((flags[u] >> j) & 1u) {
+            st[pos] = vals[u][j];
+#if WDB_NOUT == 2
+            st2[pos] = vals2[u][j];
+#endif
+            ++pos;
+          }
+        total += tot;
+      }
+    }
+    if (lane == 0) WDB_SP_WCNT(b, warp) = total;
+    __syncwarp();
+    wdb_bar_arrive(WDB_SP_BAR_CNT(b));
+    if (r >= WDB_SP_STAGES - 1) {
+      const int bo = (int)((r - (WDB_SP_STAGES - 1)) % WDB_SP_STAGES);
+      wdb_bar_sync(WDB_SP_BAR_BASE(bo));
+      wdb_sp_copy_out(bo, warp, lane, out, out2, out_cap);
+      __syncwarp();
+    }
+  }
+  for (i64 ro = nr > (WDB_SP_STAGES - 1) ? nr - (WDB_SP_STAGES - 1) : 0; ro < nr; ++ro) {   // drain
+    const int bo = (int)(ro % WDB_SP_STAGES);
+    wdb_bar_sync(WDB_SP_BAR_BASE(bo));
+    wdb_sp_copy_out(bo, warp, lane, out, out2, out_cap);
+    __syncwarp();
+  }
+}
 #endif

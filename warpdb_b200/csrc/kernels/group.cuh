@@ -212,7 +212,7 @@ struct wdb_wp_state {
 #define WDB_WP_OFF_MAXS (WDB_WP_OFF_MINS + (WDB_WP_HAS_MM ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
 #define WDB_WP_OFF_FIRST (WDB_WP_OFF_MAXS + (WDB_WP_HAS_MM ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
 #define WDB_WP_OFF_TAGS (WDB_WP_OFF_FIRST + (WDB_WP_HAS_FIRST ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
-#define WDB_WP_OFF_CNTS (WDB_WP_OFF_TAGS + 4u * WDB_WP_IDS * WDB_WP_WARPS)
+#define WDB_WP_OFF_CNTS (WDB_WP_OFF_TAGS + (WDB_WP_MODE == 1 ? 0u : 4u) * WDB_WP_IDS * WDB_WP_WARPS)
 #define WDB_WP_MIN(W, id) (*reinterpret_cast<i64 *>(wdb_wp_smem + (W).mins + 8u * (id)))
 #define WDB_WP_MAX(W, id) (*reinterpret_cast<i64 *>(wdb_wp_smem + (W).maxs + 8u * (id)))
 #define WDB_WP_FIRST(W, id) (*reinterpret_cast<i64 *>(wdb_wp_smem + (W).first + 8u * (id)))
@@ -285,6 +285,58 @@ __device__ __forceinline__ void wdb_wp_step(const wdb_table &T, const wdb_wp_sta
   }
 }
 
+#if WDB_WP_MODE == 1
+// Leader aggregation: the lanes of a warp that hit the same id in this step find each other with
+// MATCH.ANY; the lowest lane of every peer group (the leader) collects the group's values with
+// shuffles and is the only one to touch shared memory -- one LDS.64 + STS.64 per distinct id and no
+// tag round-trip (half the shared-memory wavefronts of the arbitration above, and no second round).
+// Untouched accumulators are recognised by their initial values (-0.0 sums, zero counts, +inf / -inf
+// extrema, MAX first row), so this mode keeps no tag array at all.
+template <int NI>
+__device__ __forceinline__ void wdb_wp_step_match(const wdb_table &T, const wdb_wp_state &W, const u32 lane, const int (&key)[NI],
+                                                  const float (&val)[NI], const bool (&valid)[NI], const i64 row0) {
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const u32 id = (u32)key[i] - (u32)W.key_base;
+    const bool mine = valid[i] && id < (u32)WDB_WP_IDS;
+    if (__any_sync(WDB_FULL_MASK, valid[i] && !mine)) {   // stale statistics: a key outside the promised range
+      if (valid[i] && !mine) wdb_wp_global_row(T, key[i], val[i], row0 + i);
+      __syncwarp();
+    }
+    const u32 peers = __match_any_sync(WDB_FULL_MASK, mine ? id : (0x80000000u | lane));
+    const bool leader = mine && (peers & wdb_lanemask_lt()) == 0u;
+    u32 rest = leader ? (peers & (peers - 1u)) : 0u;        // the peers above the leader
+    double acc = (double)val[i];
+    u32 cnt = 1u;
+    i64 emin = WDB_WP_HAS_MM ? wdb_f64_enc((double)val[i]) : 0, emax = emin;
+#pragma unroll 1
+    while (__any_sync(WDB_FULL_MASK, rest != 0u)) {         // rare: two rows of one warp step share a key
+      const int src = rest ? (__ffs(rest) - 1) : (int)lane;
+      const float v = __shfl_sync(WDB_FULL_MASK, val[i], src);
+      if (rest) {
+        acc += (double)v;
+        ++cnt;
+        if (WDB_WP_HAS_MM) { const i64 e = wdb_f64_enc((double)v); emin = min(emin, e); emax = max(emax, e); }
+        rest &= rest - 1u;
+      }
+    }
+    if (leader) {
+      if (WDB_WP_HAS_SUM) WDB_WP_SUM(W, id) += acc + 0.0;
+      if (WDB_WP_HAS_CNT) WDB_WP_CNT(W, id) += cnt;
+      if (WDB_WP_HAS_MM) {
+        if (emin < WDB_WP_MIN(W, id)) WDB_WP_MIN(W, id) = emin;
+        if (emax > WDB_WP_MAX(W, id)) WDB_WP_MAX(W, id) = emax;
+      }
+      if (WDB_WP_HAS_FIRST && row0 + i < WDB_WP_FIRST(W, id)) WDB_WP_FIRST(W, id) = row0 + i;   // the leader is the lowest lane = the smallest row
+    }
+    __syncwarp();
+  }
+}
+#define WDB_WP_STEP wdb_wp_step_match
+#else
+#define WDB_WP_STEP wdb_wp_step
+#endif
+
 __device__ __forceinline__ void wdb_wp_tile(const wdb_table &T, const wdb_wp_state &W, const u32 lane, const wdb_rows (&R)[WDB_UNROLL],
                                             const i64 v0, const i64 nvec, const bool full, const i64 row_base) {
 #pragma unroll
@@ -309,7 +361,7 @@ __device__ __forceinline__ void wdb_wp_tile(const wdb_table &T, const wdb_wp_sta
           val[i] = WDB_VAL(R[u], j0 + i);
         }
       }
-      wdb_wp_step<WDB_WP_ILP>(T, W, lane, key, val, valid, row + j0);
+      WDB_WP_STEP<WDB_WP_ILP>(T, W, lane, key, val, valid, row + j0);
     }
   }
 }
@@ -338,10 +390,10 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
   W.cnts = WDB_WP_OFF_CNTS + 4u * WDB_WP_IDS * warp;
   W.key_base = key_base;
   for (int s = threadIdx.x; s < WDB_WP_IDS * WDB_WP_WARPS; s += WDB_BLOCK) {
-    if (WDB_WP_HAS_SUM) all_sums[s] = 0.0;
+    if (WDB_WP_HAS_SUM) all_sums[s] = WDB_WP_MODE == 1 ? -0.0 : 0.0;
     if (WDB_WP_HAS_MM) { all_mins[s] = WDB_ENC_PLUS_INF; all_maxs[s] = WDB_ENC_MINUS_INF; }
     if (WDB_WP_HAS_FIRST) all_first[s] = 0x7fffffffffffffffll;
-    all_tags[s] = WDB_WP_NOID;
+    if (WDB_WP_MODE != 1) all_tags[s] = WDB_WP_NOID;
     if (WDB_WP_HAS_CNT) all_cnts[s] = 0u;
   }
   __syncthreads();
@@ -377,7 +429,7 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
       key[0] = WDB_KEY(R, 0);
       val[0] = WDB_VAL(R, 0);
     }
-    wdb_wp_step<1>(T, W, lane, key, val, valid, row_base + row);
+    WDB_WP_STEP<1>(T, W, lane, key, val, valid, row_base + row);
   }
   __syncthreads();
   // fold: one thread per id sums the warps' accumulators (fixed order) and adds the total to the global table
@@ -388,7 +440,17 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
     bool touched = false;
 #pragma unroll 1
     for (int w = 0; w < WDB_WP_WARPS; ++w) {
-      if (all_tags[w * WDB_WP_IDS + id] == WDB_WP_NOID) continue;
+      const int e = w * WDB_WP_IDS + id;
+#if WDB_WP_MODE == 1
+      bool hit;   // every row updates every accumulator the table tracks: any one of them tells
+      if (WDB_WP_HAS_CNT) hit = all_cnts[e] != 0u;
+      else if (WDB_WP_HAS_SUM) hit = (u64)__double_as_longlong(all_sums[e]) != WDB_DENSE_EMPTY;
+      else if (WDB_WP_HAS_MM) hit = all_mins[e] != WDB_ENC_PLUS_INF || all_maxs[e] != WDB_ENC_MINUS_INF;
+      else hit = all_first[e] != 0x7fffffffffffffffll;
+      if (!hit) continue;
+#else
+      if (all_tags[e] == WDB_WP_NOID) continue;
+#endif
       touched = true;
       if (WDB_WP_HAS_SUM) sum += all_sums[w * WDB_WP_IDS + id];
       if (WDB_WP_HAS_CNT) cnt += all_cnts[w * WDB_WP_IDS + id];

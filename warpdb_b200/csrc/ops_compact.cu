@@ -93,12 +93,19 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
   p->block = block; p->unroll = unroll; p->vec = vec; p->variant = variant;
   p->tile_rows = (int64_t)block * vec * unroll;
   p->smem = variant == 1 ? 128 + (size_t)p->tile_rows * (2 * row_bytes + 4 * (two ? 2 : 1)) : 0;
-  if (variant != 1 && p->tile_rows * 4 * (two ? 2 : 1) > 46 * 1024) return fail("compact tile of %lld rows does not fit static shared memory", (long long)p->tile_rows);
+  const int sp_stages = (int)opt("compact.sp_stages", 2);
+  if (variant == 4) {   // single pass, pipelined look-back: S staging buffers per worker warp in dynamic shared memory
+    if (sp_stages < 2 || sp_stages > 7) return fail("compact.sp_stages must be in [2,7]");
+    const int nw = block / 32;
+    p->smem = (size_t)((12 * sp_stages * nw + 15) / 16 * 16) + (size_t)sp_stages * p->tile_rows * 4 * (two ? 2 : 1);
+    if (p->smem > 227 * 1024) return fail("compact.sp_stages x compact.block needs %zu B of shared memory", p->smem);
+  }
+  if (variant != 1 && variant != 4 && p->tile_rows * 4 * (two ? 2 : 1) > 46 * 1024) return fail("compact tile of %lld rows does not fit static shared memory", (long long)p->tile_rows);
   spec.defines = {{"WDB_VEC", vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("compact.ld_hint", 0)},
                   {"WDB_ST_HINT", 0}, {"WDB_BLOCK", block}, {"WDB_UNROLL", unroll}, {"WDB_NOUT", two ? 2 : 1},
-                  {"WDB_THRESH", two ? thresh : 0}, {"WDB_MIN_CTAS", opt("compact.min_ctas", variant == 3 ? 4 : 1)},
+                  {"WDB_THRESH", two ? thresh : 0}, {"WDB_MIN_CTAS", opt("compact.min_ctas", variant == 3 ? 4 : (variant == 4 ? 3 : 1))},
                   {"WDB_LB", opt("compact.lookback", variant == 1 ? 4 : 1)}, {"WDB_BULK", variant == 1 ? 1 : 0}, {"WDB_TWOPASS", variant == 2 ? 1 : 0}, {"WDB_PRUNE", prune ? 1 : 0},
-                  {"WDB_L2PASS", variant == 3 ? 1 : 0}, {"WDB_SLAB_M", opt("compact.slab_m", 4)}, {"WDB_L2_HINTS", opt("compact.l2_hints", 1)}, {"WDB_PF_NEXT", opt("compact.pf_next", 1)}};
+                  {"WDB_L2PASS", variant >= 3 ? 1 : 0}, {"WDB_SP_STAGES", sp_stages}, {"WDB_SLAB_M", opt("compact.slab_m", 4)}, {"WDB_L2_HINTS", opt("compact.l2_hints", 1)}, {"WDB_PF_NEXT", opt("compact.pf_next", 1)}};
   if (variant == 1) spec.defines.push_back({"WDB_TILE", p->tile_rows});
   spec.fns.push_back({"expr", "float", expr});
   if (two) spec.fns.push_back({"expr2", "float", expr2});
@@ -171,8 +178,8 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
     return 0;
   }
   Kernel k;
-  const bool bulk = p.variant == 1, l2pass = p.variant == 3;
-  if (get_kernel(d, gen_source(spec), "wdb_compact.cu", bulk ? "wdb_compact_bulk" : (l2pass ? "wdb_compact_l2" : "wdb_compact"), &k)) return 1;
+  const bool bulk = p.variant == 1, l2pass = p.variant == 3, sp = p.variant == 4;
+  if (get_kernel(d, gen_source(spec), "wdb_compact.cu", bulk ? "wdb_compact_bulk" : (l2pass ? "wdb_compact_l2" : (sp ? "wdb_compact_sp" : "wdb_compact")), &k)) return 1;
 
   // variant 3 works on slabs of slab_m chunks per warp; the status words are per slab
   const int64_t slab_rows = tile_rows * std::max<int64_t>(1, opt("compact.slab_m", 4));
@@ -188,7 +195,7 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
   if (ntiles > 0) {
     if (p.smem > 48 * 1024) WDB_CUDA(cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     int nb = 0;
-    WDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)k.fn, block, p.smem));
+    WDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)k.fn, sp ? block + 32 : block, p.smem));
     if (nb < 1) return fail("compaction kernel does not fit on an SM (%zu bytes of shared memory)", p.smem);
     // the bulk variant assigns tiles statically: its grid must not exceed what is co-resident
     int64_t per_sm = std::min<int64_t>(nb, opt("compact.ctas_per_sm", 8));
@@ -201,6 +208,11 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
     if (bulk) {
       void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_cnt, &nt, &tau, &cap};
       if (launch(k, grid, block, p.smem, stream, args)) return 1;
+    } else if (sp) {   // static round-robin slabs: the grid (<= SMs x resident CTAs, above) is co-resident by construction
+      const int64_t chunk_rows = tile_rows / (block / 32);
+      long long nchunks = (n + chunk_rows - 1) / chunk_rows;
+      void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_cnt, &nt, &nchunks, &tau, &cap};
+      if (launch(k, grid, block + 32, p.smem, stream, args)) return 1;
     } else if (l2pass) {
       const int64_t chunk_rows = tile_rows / (block / 32);
       long long nchunks = (n + chunk_rows - 1) / chunk_rows;

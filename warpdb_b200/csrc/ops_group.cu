@@ -268,7 +268,7 @@ static unsigned grid_for(Device *d, long long n) {
 
 // warp-private accumulators (wdb_group_wp): bytes per key and whether at least 4 warps per SM fit
 static int64_t wp_bytes_per_id(int needs) {
-  return 4 + ((needs & WDB_NEED_SUM_BIT) ? 8 : 0) + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0) + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) +
+  return (opt("group.wp_mode", 0) == 1 ? 0 : 4) + ((needs & WDB_NEED_SUM_BIT) ? 8 : 0) + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0) + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) +
          ((needs & WDB_NEED_FIRST_BIT) ? 8 : 0);
 }
 constexpr int64_t kMaxDynSmem = 232448 - 64;   // sm_100: 227 KB per CTA
@@ -350,7 +350,7 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   spec.defines = {{"WDB_VEC", p->vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", ld_hint}, {"WDB_ST_HINT", 0}, {"WDB_DENSE", dense ? 1 : 0},
                   {"WDB_BLOCK", p->block}, {"WDB_UNROLL", p->unroll}, {"WDB_NEEDS", needs}, {"WDB_SMEM_SLOTS", slots},
                   {"WDB_SMEM_LOG2", log2}, {"WDB_SMEM_PROBES", opt("group.smem_probes", 4)}, {"WDB_HAS_COND", has_cond ? 1 : 0},
-                  {"WDB_WP_IDS", wp}, {"WDB_WP_ILP", wp_ilp}};
+                  {"WDB_WP_IDS", wp}, {"WDB_WP_ILP", wp_ilp}, {"WDB_WP_MODE", opt("group.wp_mode", 0)}};
   spec.fns.push_back({"val", "float", (needs & ~WDB_NEED_CNT_BIT & ~WDB_NEED_FIRST_BIT) ? val : "0.0f"});  // COUNT never evaluates its argument (src/warpdb.cpp:376)
   spec.fns.push_back({"key", "int", key});
   if (has_cond) spec.fns.push_back({"cond", "bool", cond});
