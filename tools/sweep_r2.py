@@ -63,10 +63,12 @@ def sweep_compact(n):
     out = torch.empty(n, dtype=torch.float32, device="cuda")
     expr, cond = "(price[idx] * 0.9f)", "(price[idx] > 20.0f)"
     cfgs = [{"compact.variant": 3}]
-    for stages in (2, 3):
-        for block, mc in ((256, 3), (256, 2), (128, 4), (512, 1)):
-            for lb in (1, 4, 8):
-                cfgs.append({"compact.variant": 4, "compact.sp_stages": stages, "compact.block": block, "compact.min_ctas": mc, "compact.lookback": lb})
+    # the look-back chain advances one window per L2 round trip: window x slab bytes / RTT bounds the kernel
+    for lb in (1, 2, 4, 8):
+        for slab_m in (4, 8, 2):
+            for mc in (4, 3):
+                if (lb, slab_m, mc) != (1, 4, 4):
+                    cfgs.append({"compact.variant": 3, "compact.lookback": lb, "compact.slab_m": slab_m, "compact.min_ctas": mc})
     best = {}
     for sel in (0.01, 0.5, 0.99):
         price = ops.synth_f32(n, 0xC0FFEE + 3, 0.0, 20.0 / (1.0 - sel))

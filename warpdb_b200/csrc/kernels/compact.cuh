@@ -783,6 +783,9 @@ wdb_compact_l2(const wdb_cols C, float *__restrict__ out, float *__restrict__ ou
 #ifndef WDB_SP_STAGES
 #define WDB_SP_STAGES 2
 #endif
+#ifndef WDB_SP_SCAN
+#define WDB_SP_SCAN 1
+#endif
 #define WDB_SP_THREADS (WDB_BLOCK + 32)
 __device__ __forceinline__ void wdb_bar_arrive(const int id) { asm volatile("barrier.arrive %0, %1;" :: "r"(id), "n"(WDB_SP_THREADS) : "memory"); }
 __device__ __forceinline__ void wdb_bar_sync(const int id) { asm volatile("barrier.sync %0, %1;" :: "r"(id), "n"(WDB_SP_THREADS) : "memory"); }
@@ -815,21 +818,66 @@ __device__ __forceinline__ void wdb_sp_copy_out(const int b, const u32 warp, con
 }
 
 extern "C" __global__ void __launch_bounds__(WDB_SP_THREADS, WDB_MIN_CTAS)
-wdb_compact_sp(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n, u64 *__restrict__ status,
-               i64 *__restrict__ out_count, const i64 nslabs, const i64 nchunks, const float wdb_tau, const i64 out_cap) {
+wdb_compact_sp(const wdb_cols C, float *__restrict__ out, float *__restrict__ out2, const i64 n, u64 *__restrict__ status, u64 *__restrict__ rbase,
+               u32 *__restrict__ ticket, i64 *__restrict__ out_count, const i64 nslabs, const i64 nchunks, const float wdb_tau, const i64 out_cap) {
   const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const i64 first = blockIdx.x;
-  const i64 nr = first < nslabs ? (nslabs - first + gridDim.x - 1) / gridDim.x : 0;   // rounds of this CTA
+  // Slab of round r.  WDB_SP_SCAN == 1: static round-robin (round-synchronous prefix).  Otherwise the first
+  // S rounds are static and every later one is a ticket the scanner drew S rounds earlier (slabs are
+  // then handed out in time order: whatever a slab's look-back waits for was started before it, so a
+  // late CTA delays nobody but itself) and parked in s_slab[r % 2S]; the workers pick it up behind the
+  // BASE barrier of round r - S, which they pass before they start round r.
+  __shared__ i64 s_slab[2 * WDB_SP_STAGES];
+#if WDB_SP_SCAN == 1
+#define WDB_SP_SLAB(r) ((i64)blockIdx.x + (r) * (i64)gridDim.x)
+#else
+#define WDB_SP_SLAB(r) ((r) < WDB_SP_STAGES ? (i64)blockIdx.x + (r) * (i64)gridDim.x : s_slab[(r) % (2 * WDB_SP_STAGES)])
+#endif
   if (warp == WDB_NWARPS) {
     // ---- scanner warp: counts of round r -> global offsets of round r
-    for (i64 r = 0; r < nr; ++r) {
+    for (i64 r = 0;; ++r) {
       const int b = (int)(r % WDB_SP_STAGES);
-      const i64 slab = first + r * gridDim.x;
+      const i64 slab = WDB_SP_SLAB(r);
+      if (slab >= nslabs) break;
+#if WDB_SP_SCAN != 1
+      if (lane == 0) s_slab[(r + WDB_SP_STAGES) % (2 * WDB_SP_STAGES)] = WDB_SP_STAGES * (i64)gridDim.x + (i64)atomicAdd(ticket, 1u);   // published by this round's BASE arrive
+#endif
       wdb_bar_sync(WDB_SP_BAR_CNT(b));
       const u32 c = lane < WDB_NWARPS ? WDB_SP_WCNT(b, lane) : 0u;
       u32 pre, ttotal;
       wdb_warp_rank(c, lane, pre, ttotal);
       i64 excl = 0;
+#if WDB_SP_SCAN == 1
+      // Round-synchronous prefix: the offset of (r, c) is rbase[r] + the aggregates of (r, 0 .. c-1), all read
+      // in parallel.  Measured SLOWER than the decoupled look-back: every round becomes a grid-wide
+      // barrier in disguise, and with round-robin slabs one late CTA stalls all the others.
+      {
+        const i64 slab0 = r * gridDim.x;
+        if (lane == 0) wdb_st_status(&status[slab], (WDB_ST_AGG << 62) | (u64)ttotal);
+        u64 sum = 0;
+        const i64 c0 = (i64)blockIdx.x;
+        for (i64 i = lane; i < c0; i += 128) {
+          u64 st[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) st[q] = (i + 32 * q < c0) ? wdb_ld_status(&status[slab0 + i + 32 * q]) : (WDB_ST_AGG << 62);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            while ((st[q] >> 62) == 0ull) st[q] = wdb_ld_status(&status[slab0 + i + 32 * q]);
+            sum += st[q] & WDB_ST_MASK;
+          }
+        }
+        u64 base = 0;
+        if (r > 0) {
+          if (lane == 0) {
+            u64 st;
+            do { st = wdb_ld_status(&rbase[r]); } while ((st >> 62) == 0ull);
+            base = st & WDB_ST_MASK;
+          }
+          base = __shfl_sync(WDB_FULL_MASK, base, 0);
+        }
+        excl = (i64)(base + wdb_warp_sum64(sum));
+        if (blockIdx.x == gridDim.x - 1 && lane == 0) wdb_st_status(&rbase[r + 1], (WDB_ST_AGG << 62) | (u64)(excl + (i64)ttotal));
+      }
+#else
       if (slab == 0) {
         if (lane == 0) wdb_st_status(&status[0], (WDB_ST_PREFIX << 62) | (u64)ttotal);
       } else {
@@ -837,6 +885,7 @@ wdb_compact_sp(const wdb_cols C, float *__restrict__ out, float *__restrict__ ou
         excl = wdb_lookback(status, slab, lane);
         if (lane == 0) wdb_st_status(&status[slab], (WDB_ST_PREFIX << 62) | (u64)(excl + (i64)ttotal));
       }
+#endif
       if (lane < WDB_NWARPS) WDB_SP_GOFF(b, lane) = excl + (i64)pre;
       if (lane == 0 && slab == nslabs - 1) *out_count = excl + (i64)ttotal;
       __syncwarp();
@@ -845,9 +894,13 @@ wdb_compact_sp(const wdb_cols C, float *__restrict__ out, float *__restrict__ ou
     return;
   }
   // ---- worker warps
-  for (i64 r = 0; r < nr; ++r) {
+  i64 nr = 0;
+  for (i64 r = 0;; ++r) {
     const int b = (int)(r % WDB_SP_STAGES);
-    const i64 chunk = (first + r * gridDim.x) * WDB_NWARPS + warp;
+    const i64 slab = WDB_SP_SLAB(r);
+    if (slab >= nslabs) break;
+    nr = r + 1;
+    const i64 chunk = slab * WDB_NWARPS + warp;
     u32 total = 0;
     if (chunk < nchunks) {
       u32 flags[WDB_UNROLL];

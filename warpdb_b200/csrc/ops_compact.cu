@@ -105,7 +105,7 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
                   {"WDB_ST_HINT", 0}, {"WDB_BLOCK", block}, {"WDB_UNROLL", unroll}, {"WDB_NOUT", two ? 2 : 1},
                   {"WDB_THRESH", two ? thresh : 0}, {"WDB_MIN_CTAS", opt("compact.min_ctas", variant == 3 ? 4 : (variant == 4 ? 3 : 1))},
                   {"WDB_LB", opt("compact.lookback", variant == 1 ? 4 : 1)}, {"WDB_BULK", variant == 1 ? 1 : 0}, {"WDB_TWOPASS", variant == 2 ? 1 : 0}, {"WDB_PRUNE", prune ? 1 : 0},
-                  {"WDB_L2PASS", variant >= 3 ? 1 : 0}, {"WDB_SP_STAGES", sp_stages}, {"WDB_SLAB_M", opt("compact.slab_m", 4)}, {"WDB_L2_HINTS", opt("compact.l2_hints", 1)}, {"WDB_PF_NEXT", opt("compact.pf_next", 1)}};
+                  {"WDB_L2PASS", variant >= 3 ? 1 : 0}, {"WDB_SP_STAGES", sp_stages}, {"WDB_SP_SCAN", opt("compact.sp_scan", 0)}, {"WDB_SLAB_M", opt("compact.slab_m", 4)}, {"WDB_L2_HINTS", opt("compact.l2_hints", 1)}, {"WDB_PF_NEXT", opt("compact.pf_next", 1)}};
   if (variant == 1) spec.defines.push_back({"WDB_TILE", p->tile_rows});
   spec.fns.push_back({"expr", "float", expr});
   if (two) spec.fns.push_back({"expr2", "float", expr2});
@@ -184,8 +184,9 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
   // variant 3 works on slabs of slab_m chunks per warp; the status words are per slab
   const int64_t slab_rows = tile_rows * std::max<int64_t>(1, opt("compact.slab_m", 4));
   const int64_t ntiles = l2pass ? (n + slab_rows - 1) / slab_rows : (n + tile_rows - 1) / tile_rows;
-  // scratch: [0,8) survivor count, [8,12) ticket, [64, 64+8*ntiles) tile status words
-  const size_t need = 64 + (size_t)std::max<int64_t>(ntiles, 1) * 8;
+  // scratch: [0,8) survivor count, [8,12) ticket, [64, 64+8*ntiles) tile status words (+ one word per round of
+  // the single-pass variant: at least one slab per CTA and round, so ntiles + 2 words always suffice)
+  const size_t need = 64 + (size_t)std::max<int64_t>(ntiles, 1) * 8 + (sp ? (size_t)(ntiles + 2) * 8 : 0);
   char *sc = nullptr;
   WDB_CUDA(cudaMallocAsync((void **)&sc, need, stream));
   WDB_CUDA(cudaMemsetAsync(sc, 0, need, stream));
@@ -211,7 +212,8 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
     } else if (sp) {   // static round-robin slabs: the grid (<= SMs x resident CTAs, above) is co-resident by construction
       const int64_t chunk_rows = tile_rows / (block / 32);
       long long nchunks = (n + chunk_rows - 1) / chunk_rows;
-      void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_cnt, &nt, &nchunks, &tau, &cap};
+      unsigned long long *d_rbase = d_status + std::max<int64_t>(ntiles, 1);
+      void *args[] = {ptrs.data(), &d_out, &d_out2, &nn, &d_status, &d_rbase, &d_ticket, &d_cnt, &nt, &nchunks, &tau, &cap};
       if (launch(k, grid, block + 32, p.smem, stream, args)) return 1;
     } else if (l2pass) {
       const int64_t chunk_rows = tile_rows / (block / 32);

@@ -305,9 +305,11 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   int64_t slots = opt("group.smem_slots", -1);
   if (dense && !use_wp) {   // in-range rows go straight to the direct-addressed table: one RED each, nothing to pre-aggregate
     slots = 0;
-    p->block = (int)opt("group.dense_block", 512);
+    // profiles/r02_sweep_group10m.jsonl: few, small CTAs keep fewer REDs in flight per SM and the table slice
+    // in the L2 (256 threads x 128-bit loads, 2 CTAs per SM: 6.25 ms per 1e9 rows at 10 M keys against 6.72 ms)
+    p->block = (int)opt("group.dense_block", 256);
     p->unroll = (int)opt("group.dense_unroll", 1);
-    p->vec = (int)opt("group.dense_vec", 8);
+    p->vec = (int)opt("group.dense_vec", 4);
   }
   if (slots < 0) {
     slots = 0;
@@ -633,7 +635,7 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   if (p.smem_bytes > 48 * 1024) WDB_CUDA(cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
   int nb = 0;
   WDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)k.fn, p.block, p.smem_bytes));
-  nb = std::max(1, std::min<int>(nb, (int)opt("group.ctas_per_sm", 8)));
+  nb = std::max(1, std::min<int>(nb, (int)opt("group.ctas_per_sm", (t->dense_live && p.wp_ids == 0) ? 2 : 8)));
   const int64_t tile_rows = (int64_t)p.block * p.unroll * p.vec;
   const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
   unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)d->num_sms * nb));
