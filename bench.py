@@ -57,12 +57,13 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_per_row(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per row of the committed `ncu --set full` capture
-    (profiles/traffic.json; measured once per kernel, scaled by rows here -- it is NOT measured in this run)."""
+def traffic_per_row(kernel, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per row and LAUNCH of the committed `ncu --set full` capture
+    of this kernel on this workload at this size (profiles/traffic.json <- profiles/r02_ncu_full_summary.csv);
+    scaled by the rows of the launch here -- it is NOT measured in this run."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        k = t["kernels"].get(kernel)
+        k = t["kernels"].get(f"{kernel}:{workload}")
         return (k["dram_bytes_per_row"], t.get("source", "profiles/traffic.json")) if k else (None, None)
     except Exception:  # noqa: BLE001
         return None, None
@@ -202,12 +203,12 @@ def time_steps(step, steps, warmup, world, sampler=None):
     return max_over_ranks(a.elapsed_time(b), world), launches, clocks
 
 
-def roofline(kernel, bytes_per_row, rows, kernel_ms, peak, peak_src, note=None):
+def roofline(kernel, workload, bytes_per_row, rows, kernel_ms, peak, peak_src, note=None):
     achieved = bytes_per_row * rows / (kernel_ms * 1e-3) / 1e9
-    tpr, tsrc = traffic_per_row(kernel)
+    tpr, tsrc = traffic_per_row(kernel, workload)
     r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
          "traffic": tpr * rows if tpr else None,
-         "traffic_source": (f"{tsrc}: {tpr:.3f} DRAM bytes per row x rows of this launch (ncu capture, not measured in this run)" if tpr else None),
+         "traffic_source": (f"{tsrc}: {tpr:.3f} DRAM bytes per row and launch x rows of this launch (ncu capture of this workload, not measured in this run)" if tpr else None),
          "kernel": kernel, "kernel_ms": kernel_ms, "peak_source": peak_src, "frac_of_8TBs_spec": achieved / 8000.0,
          "algorithmic_bytes_per_row": bytes_per_row, "algorithmic_bytes_per_launch": bytes_per_row * rows}
     if note:
@@ -260,7 +261,7 @@ def run_filter(name, args, rank, world, local, comm, comm1, sampler, peak, peak_
     rec = {"query": "SELECT price * 0.9 FROM t WHERE price > 20 (stable compaction)", "baseline_config": "configs[2]", "selectivity": s,
            "rows_total": total, "rows_per_gpu": rows, "scaling": "strong" if world > 1 else "n/a", "ms_per_step": per,
            "value": total / (per * 1e-3), "unit": "rows/s",
-           "roofline": roofline("wdb_compact_l2", bpr, rows, ms_local / args.steps, peak, peak_src,
+           "roofline": roofline("wdb_compact_l2", name, bpr, rows, ms_local / args.steps, peak, peak_src,
                                 "kernel_ms = the local compaction call (wdb_compact_l2 + its 1-CTA finish kernel) timed with CUDA events"),
            "merge_ms": max(per - ms_local / args.steps, 0.0), "collectives": ["ncclAllGather(1 x int64 per rank: survivor counts)"] if world > 1 else [],
            "gpu_launches": launches, "clocks": clocks, "result_checked": ok}
@@ -327,7 +328,7 @@ def run_group(name, args, rank, world, local, comm, comm1, sampler, peak, peak_s
     rec = {"query": "SELECT SUM(price) FROM t GROUP BY quantity", "baseline_config": "configs[3]", "groups": G,
            "rows_total": total, "rows_per_gpu": rows, "scaling": "strong" if world > 1 else "n/a", "ms_per_step": per,
            "value": total / (per * 1e-3), "unit": "rows/s",
-           "roofline": roofline(kernel, 8.0, rows, kernel_ms, peak, peak_src, "kernel_ms = the consume launch(es) alone; the step adds table reset, all-reduce and ordered export"),
+           "roofline": roofline(kernel, name, 8.0, rows, kernel_ms, peak, peak_src, "kernel_ms = the consume launch(es) alone; the step adds table reset, all-reduce and ordered export"),
            "local_ms": ms_local / args.steps, "merge_ms": max(per - ms_local / args.steps, 0.0),
            "collectives": [f"ncclAllReduce(sum, float64 x {rng[1] - rng[0] + 1}: direct-addressed partial sums)"] if world > 1 else [],
            "merge_bytes_per_gpu": 8 * (rng[1] - rng[0] + 1) if world > 1 else 0,
@@ -368,7 +369,7 @@ def run_topk(name, args, rank, world, local, comm, comm1, sampler, peak, peak_sr
     rec = {"query": "SELECT discount(price, 0.9) FROM t ORDER BY discount(price, 0.9) DESC LIMIT 5 (custom.cu UDF)", "baseline_config": "configs[4]",
            "rows_total": total, "rows_per_gpu": rows, "scaling": "strong" if world > 1 else "n/a", "ms_per_step": per,
            "value": total / (per * 1e-3), "unit": "rows/s",
-           "roofline": roofline("wdb_topk_scan", 4.0, rows, ms_local / args.steps, peak, peak_src,
+           "roofline": roofline("wdb_topk_scan", name, 4.0, rows, ms_local / args.steps, peak, peak_src,
                                 "kernel_ms = the local step (wdb_topk_scan + the 1-CTA final and emit kernels, ~15 us) timed with CUDA events"),
            "merge_ms": max(per - ms_local / args.steps, 0.0),
            "collectives": ["ncclAllGather(80 B per rank: 5 x (key f32, value f32, global row i64))"] if world > 1 else [],
@@ -420,13 +421,52 @@ def e2e_projection(rows, steps, warmup, world, rank, local):
         dt = time.perf_counter() - t0
         idx = torch.randint(0, n, (1 << 20,))
         ok = bool(torch.equal(ho[idx], (hp[idx] * hq[idx].float()) * 1.08)) and bool(torch.equal(ho[-(1 << 16):], (hp[-(1 << 16):] * hq[-(1 << 16):].float()) * 1.08))
+        yard = pcie_yardstick(hp, ho, world)   # after the check: it overwrites the head of ho
         res = dict(value=n * steps / dt, unit="rows/s", h2d_bytes_per_step=8 * n, d2h_bytes_per_step=4 * n,
                    steps=steps, ms_per_step=dt / steps * 1e3, result_checked=ok, pcie_gbs=12.0 * n * steps / dt / 1e9,
+                   pcie_yardstick=yard,
+                   pcie_bound_rows_per_s=(min(yard["duplex_h2d_gbs"] / 8.0, yard["duplex_d2h_gbs"] / 4.0) * 1e9 if "duplex_h2d_gbs" in yard else None),
                    api=f"one call of wdb_multi_project_filter_host(ndev={world}) per step from ONE process (run_multi_gpu_jit_host replacement), pinned host buffers, "
                        "wall clock around the calls (the call returns when the results are on the host)")
         del hp, hq, ho
     barrier(world)
     return res
+
+
+def pcie_yardstick(h_src, h_dst, ndev, mb=1024):
+    """What the box's PCIe links deliver with plain cudaMemcpyAsync from / to the same pinned buffers on all
+    ndev GPUs at once (one process, one stream per direction and device): H2D alone, D2H alone, both together.
+    The projection moves 8 B/row up and 4 B/row down, so its end-to-end ceiling is
+    min(duplex_h2d / 8, duplex_d2h / 4) rows/s (`pcie_bound_rows_per_s`)."""
+    import torch
+    try:
+        m = mb * (1 << 20) // 4
+        devs = list(range(ndev))
+        dbuf = [(torch.empty(m, dtype=torch.float32, device=f"cuda:{d}"), torch.empty(m, dtype=torch.float32, device=f"cuda:{d}")) for d in devs]
+        up = [torch.cuda.Stream(device=d) for d in devs]
+        down = [torch.cuda.Stream(device=d) for d in devs]
+
+        def run(do_up, do_down, reps=3):
+            for d in devs:
+                torch.cuda.synchronize(d)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                for d in devs:
+                    if do_up:
+                        with torch.cuda.stream(up[d]):
+                            dbuf[d][0].copy_(h_src[d * m:(d + 1) * m], non_blocking=True)
+                    if do_down:
+                        with torch.cuda.stream(down[d]):
+                            h_dst[d * m:(d + 1) * m].copy_(dbuf[d][1], non_blocking=True)
+            for d in devs:
+                torch.cuda.synchronize(d)
+            return reps * ndev * m * 4 / (time.perf_counter() - t0) / 1e9
+        run(True, True, 1)
+        h2d, d2h, both = run(True, False), run(False, True), run(True, True)
+        return {"h2d_gbs": h2d, "d2h_gbs": d2h, "duplex_h2d_gbs": both, "duplex_d2h_gbs": both, "n_gpus": ndev, "mb_per_copy": mb,
+                "how": "torch copy_(non_blocking) of pinned slices, all GPUs concurrently from one process, 3 repetitions, aggregate GB/s per direction"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
 
 
 def cpu_baseline_projection(sample_rows, steps=1):
@@ -512,7 +552,7 @@ def run_ours(args):
                    "rows_per_gpu": rows, "sharding": "contiguous row ranges, one process per GPU, no data-path collective",
                    "l2": "inputs (>= 4 GB per column) are far larger than the 126 MB L2; no flush needed",
                    "algorithmic_bytes_per_row": 12.0, "result_checked": ok},
-        "roofline": roofline("wdb_project", 12.0, rows, ms_per_step, peak, peak_src),
+        "roofline": roofline("wdb_project", "projection", 12.0, rows, ms_per_step, peak, peak_src),
         "gpu_launches": launches, "clocks": clocks, "nvrtc_compile_ms_untimed": compile_ms,
     }
     line["gbs_per_gpu"] = line["roofline"]["achieved"]

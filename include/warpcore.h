@@ -171,6 +171,15 @@ int wdb_project_filter_pruned(int device, void *stream, const wdb_col_t *cols, i
                               const char *cond, float *d_out, int64_t n, int mode, int64_t *d_count,
                               int64_t *h_count, const wdb_prune_t *preds, int npreds, int64_t *h_zones_live);
 
+/* The same pruning for GROUP BY and ORDER BY ... LIMIT with a WHERE clause: the kernels run over the
+ * maximal runs of live zones only (few, long runs on sorted / clustered columns; on a random layout the
+ * plain call is taken).  Results are identical to wdb_agg_consume / wdb_topk. */
+int wdb_agg_consume_pruned(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols, const char *val_expr, const char *key_expr,
+                           const char *cond, int64_t n, int64_t row_base, const wdb_prune_t *preds, int npreds, int64_t *h_zones_live);
+int wdb_topk_pruned(int device, void *stream, const wdb_col_t *cols, int ncols, const char *key_expr, const char *val_expr, const char *cond,
+                    int descending, int64_t k, int64_t offset, int64_t n, float *d_out_vals, float *d_out_keys, int64_t *h_n,
+                    const wdb_prune_t *preds, int npreds, int64_t *h_zones_live);
+
 /* ---- multi-GPU: run_multi_gpu_jit_host (include/multi_gpu_utils.hpp:10-12,
  * src/multi_gpu_utils.cpp:5-63).  Host columns in, host floats out; rows are split into
  * contiguous shards chunk = ceil(n/ndev) and all devices run concurrently on their own

@@ -96,3 +96,45 @@ def test_cli(pw):
     exe = os.path.join(ROOT, "warpdb_b200", "warpdb")
     r = subprocess.run([exe, "price * quantity WHERE price > 10", "test.csv"], cwd=DATA, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "JIT Result[3] = 150" in r.stdout, r.stdout + r.stderr
+
+
+def test_group_by_several_keys(pw, tmp_path):
+    """GROUP BY a, b: the reference parses the key list (include/expression.hpp:128-130) but reads keys[0] only
+    (src/warpdb.cpp:362,374); here integer key columns fold into one composite key and the groups come back in
+    lexicographic (a, b) order.  Checked against a NumPy group-by (this is beyond what the reference, and hence
+    the oracle, computes)."""
+    rng = np.random.default_rng(5)
+    n = 20_000
+    price = rng.uniform(0, 100, n).astype(np.float32)
+    a = rng.integers(-3, 9, n).astype(np.int32)
+    b = rng.integers(100, 140, n).astype(np.int32)
+    path = tmp_path / "multi.csv"
+    with open(path, "w") as f:
+        f.write("price,a,b\n")
+        for p, x, y in zip(price, a, b):
+            f.write(f"{float(p)!r},{x},{y}\n")
+    db = pw.WarpDB(str(path), [pw.DataType.Float32, pw.DataType.Int32, pw.DataType.Int32])
+    comp = (a.astype(np.int64) + 3) * 40 + (b - 100)
+    for where, mask in (("", np.ones(n, bool)), (" WHERE price > 50", price > 50)):
+        keys = np.unique(comp[mask])
+        sums = np.array([price[mask & (comp == k)].astype(np.float64).sum() for k in keys])
+        cnts = np.array([(mask & (comp == k)).sum() for k in keys], np.float64)
+        mx = np.array([price[mask & (comp == k)].max() for k in keys], np.float32)
+        got = np.array(db.query_sql(f"SELECT SUM(price) FROM t{where} GROUP BY a, b"), np.float32)
+        assert got.shape == sums.shape
+        np.testing.assert_allclose(got, sums.astype(np.float32), rtol=1e-6)
+        assert np.array_equal(np.array(db.query_sql(f"SELECT COUNT(price) FROM t{where} GROUP BY a, b"), np.float32), cnts.astype(np.float32))
+        assert np.array_equal(np.array(db.query_sql(f"SELECT MAX(price) FROM t{where} GROUP BY a, b ORDER BY a DESC"), np.float32), mx[::-1])
+    with pytest.raises(RuntimeError, match="integer columns"):
+        db.query_sql("SELECT SUM(price) FROM t GROUP BY a, price")
+
+
+def test_multi_gpu_sql_surface(pw):
+    """query_sql_multi_gpu: aggregates / ORDER BY ... LIMIT over row-range shards of the host table, merged inside the core."""
+    db = pw.WarpDB("test.csv", [pw.DataType.Float32, pw.DataType.Int32])
+    assert db.query_sql_multi_gpu("SELECT SUM(price) FROM test GROUP BY quantity ORDER BY quantity ASC") == [15.25, 10.5, 20.0, 30.0]
+    assert db.query_sql_multi_gpu("SELECT AVG(price) FROM test GROUP BY quantity ORDER BY quantity DESC") == [30.0, 20.0, 10.5, 15.25]
+    assert db.query_sql_multi_gpu("SELECT price FROM test ORDER BY price DESC LIMIT 2") == [30.0, 20.0]
+    assert db.query_sql_multi_gpu("SELECT price * 2 FROM test WHERE price > 11") == [40.0, 30.5, 60.0]
+    with pytest.raises(RuntimeError, match="needs a LIMIT"):
+        db.query_sql_multi_gpu("SELECT price FROM test ORDER BY price DESC")

@@ -69,3 +69,47 @@ def test_int_column_compared_as_float_is_never_wrongly_pruned():
     out, cnt, live = ops.project_filter_pruned(d, "q[idx]", "(q[idx] == 16777216.0f)", [(z, "==", 16777216.0)], wc.COMPACT)
     plain, cnt_plain = ops.project_filter(d, "q[idx]", "(q[idx] == 16777216.0f)", wc.COMPACT)
     assert cnt == cnt_plain == 8192 and live == z.nzones
+
+
+@pytest.mark.parametrize("layout", ["sorted", "clustered", "random"])
+def test_pruned_group_by_and_topk_equal_the_plain_calls(layout):
+    """GROUP BY / ORDER BY ... LIMIT with a WHERE clause over a zone-mapped table run on the live runs only."""
+    n = 1_000_003
+    price = orc.synth_f32(n, 91, 0.0, 100.0)
+    qty = orc.synth_i32(n, 92, 0, 50)
+    if layout == "sorted":
+        price = np.sort(price)
+    elif layout == "clustered":
+        band = ((np.arange(n) // 10000).astype(np.int64) * 7919) % 97
+        price = (band + price / 100.0).astype(np.float32)
+    t = {"price": np.ascontiguousarray(price), "quantity": qty}
+    d = {k: torch.from_numpy(v).cuda() for k, v in t.items()}
+    zp = ops.ZoneMap(d["price"], "price")
+    for where, preds in [("price > 90", [(zp, ">", 90.0)]), ("price >= 10 AND price < 12.5", [(zp, ">=", 10.0), (zp, "<", 12.5)]),
+                         ("price > 1000", [(zp, ">", 1000.0)])]:
+        c = orc.Expr(where).cuda()
+        for agg, needs in ((wc.SUM, wc.NEED_SUM), (wc.MIN, wc.NEED_MINMAX), (wc.COUNT, wc.NEED_COUNT)):
+            r = orc.group_agg("price", "quantity", where, t, agg=agg)
+            tab = ops.AggTable(0, 64, needs)
+            live = tab.consume(d, "price[idx]", "quantity[idx]", c, preds=preds)
+            out = tab.export(agg, wc.ORDER_KEY_ASC)
+            tab.close()
+            assert np.array_equal(out["keys"].cpu().numpy(), r["keys"]), (layout, where, agg)
+            if agg == wc.SUM:
+                np.testing.assert_allclose(out["vals"].cpu().numpy(), r["vals"], rtol=1e-6)
+            else:
+                assert np.array_equal(bits(out["vals"].cpu().numpy()), bits(r["vals"]))
+            if layout == "sorted" and where == "price > 90":
+                assert live < 0.15 * zp.nzones
+        # first-appearance order needs global row ids: every run is consumed with its own row_base
+        r = orc.group_agg("price", "quantity", where, t, agg=orc.SUM, order=orc.ORDER_FIRST)
+        tab = ops.AggTable(0, 64, wc.NEED_SUM | wc.NEED_FIRST_ROW)
+        tab.consume(d, "price[idx]", "quantity[idx]", c, preds=preds)
+        out = tab.export(wc.SUM, wc.ORDER_FIRST)
+        tab.close()
+        assert np.array_equal(out["keys"].cpu().numpy(), r["keys"]), (layout, where)
+        for desc in (True, False):
+            for k, off in ((5, 0), (7, 3)):
+                want = orc.query_sql(f"SELECT price * 2 FROM t WHERE {where} ORDER BY quantity {'DESC' if desc else 'ASC'} LIMIT {k} OFFSET {off}", t)
+                got = ops.topk(d, "quantity[idx]", "(price[idx] * 2.0f)", c, desc, k, off, preds=preds).cpu().numpy()
+                assert np.array_equal(bits(got), bits(want)), (layout, where, desc, k, off)

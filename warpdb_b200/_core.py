@@ -23,7 +23,7 @@ SYMBOLS = [
     "wdb_set_option", "wdb_get_option", "wdb_get_stats", "wdb_project_filter", "wdb_agg_create", "wdb_agg_destroy",
     "wdb_agg_reset", "wdb_agg_set_key_range", "wdb_agg_consume", "wdb_agg_merge", "wdb_agg_size", "wdb_agg_spilled", "wdb_agg_export", "wdb_group_agg",
     "wdb_topk", "wdb_sort_float", "wdb_sort_pairs", "wdb_column_minmax", "wdb_multi_project_filter_host",
-    "wdb_zonemap_build", "wdb_upload_column", "wdb_zonemap_destroy", "wdb_zonemap_info", "wdb_project_filter_pruned",
+    "wdb_zonemap_build", "wdb_upload_column", "wdb_zonemap_destroy", "wdb_zonemap_info", "wdb_project_filter_pruned", "wdb_agg_consume_pruned", "wdb_topk_pruned",
     "wdb_shard_range", "wdb_synth_f32", "wdb_synth_i32", "wdb_debug_compile", "wdb_free",
     "wdb_comm_unique_id", "wdb_comm_init_rank", "wdb_comm_init_all", "wdb_comm_destroy", "wdb_comm_info",
     "wdb_multi_project_filter", "wdb_multi_group_agg", "wdb_multi_topk", "wdb_multi_group_agg_host", "wdb_multi_topk_host",
@@ -92,6 +92,8 @@ def lib():
     L.wdb_zonemap_destroy.argtypes = [vp]
     L.wdb_zonemap_info.argtypes = [vp, P64, P64]
     L.wdb_project_filter_pruned.argtypes = [ci, vp, PC, ci, cp, cp, vp, i64, ci, vp, P64, C.POINTER(Prune), ci, P64]
+    L.wdb_agg_consume_pruned.argtypes = [vp, vp, PC, ci, cp, cp, cp, i64, i64, C.POINTER(Prune), ci, P64]
+    L.wdb_topk_pruned.argtypes = [ci, vp, PC, ci, cp, cp, cp, ci, i64, i64, i64, vp, vp, P64, C.POINTER(Prune), ci, P64]
     L.wdb_shard_range.argtypes = [i64, ci, ci, P64, P64]
     L.wdb_synth_f32.argtypes = [ci, vp, vp, i64, C.c_uint64, C.c_float, C.c_float, i64]
     L.wdb_synth_i32.argtypes = [ci, vp, vp, i64, C.c_uint64, C.c_int32, C.c_int32, i64]

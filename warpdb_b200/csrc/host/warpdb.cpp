@@ -273,16 +273,22 @@ void *WarpDB::zonemap_for(const std::string &column) {
   return zm;
 }
 
+// zone-map terms of a WHERE clause as the core wants them (empty when pruning is off or does not apply)
+std::vector<wdb_prune_t> WarpDB::prune_preds(const ASTNode *cond_ast) {
+  std::vector<wdb_prune_t> preds;
+  if (zone_pruning_ && cond_ast && table_.num_rows >= 8192)
+    for (const auto &t : prune_terms(cond_ast))
+      if (void *zm = zonemap_for(t.column)) preds.push_back(wdb_prune_t{static_cast<const wdb_zonemap_t *>(zm), t.op, t.value});
+  return preds;
+}
+
 // fused filter+project of the whole table, zone-pruned when the condition allows it
 int WarpDB::filter_project(const std::string &expr, const std::string &cond, const ASTNode *cond_ast, float *d_out, int mode,
                            long long *count) {
   const std::vector<wdb_col_t> dcols = describe(table_);
   int64_t cnt = 0;
   last_zones_live_ = last_zones_total_ = -1;
-  std::vector<wdb_prune_t> preds;
-  if (zone_pruning_ && cond_ast && table_.num_rows >= 8192)
-    for (const auto &t : prune_terms(cond_ast))
-      if (void *zm = zonemap_for(t.column)) preds.push_back(wdb_prune_t{static_cast<const wdb_zonemap_t *>(zm), t.op, t.value});
+  const std::vector<wdb_prune_t> preds = prune_preds(cond_ast);
   int rc;
   if (!preds.empty()) {
     int64_t live = 0, zr = 0, nz = 0;
@@ -351,37 +357,81 @@ std::vector<float> WarpDB::query_sql(const std::string &sql) {
     if (ast.group_by->keys.empty()) throw std::runtime_error("GROUP BY needs a key");
     int needs = needs_of(agg->agg);
     if (ast.having) collect_needs(ast.having->get(), &needs);
-    const std::string val = agg->expr->to_cuda_expr(), key = ast.group_by->keys[0]->to_cuda_expr();
+    const std::string val = agg->expr->to_cuda_expr();
+    std::string key = ast.group_by->keys[0]->to_cuda_expr();
     // groups come back in key order (std::map, src/warpdb.cpp:425); ORDER BY with GROUP BY sorts by
     // key in the requested direction whatever its expression is (jit_sort_pairs, :370-371)
     const int order = (ast.order_by && !ast.order_by->ascending) ? WDB_ORDER_KEY_DESC : WDB_ORDER_KEY_ASC;
     int64_t expect = 1 << 16, groups = 0;
     // optimizer statistics (TableStats): GROUP BY on a bare integer column -> its min/max bounds the
-    // number of groups and lets the core index its accumulators directly (cached per column)
+    // number of groups and lets the core index its accumulators directly (gathered at ingest, else cached here)
     bool have_range = false;
     int64_t key_lo = 0, key_hi = -1;
-    if (const auto *kv = dynamic_cast<const VariableNode *>(ast.group_by->keys[0].get())) {
+    auto int_column_range = [&](const ASTNode *k, long long *lo, long long *hi) {
+      const auto *kv = dynamic_cast<const VariableNode *>(k);
+      if (!kv || n == 0) return false;
       for (const auto &c : table_.columns) {
-        if (c.name != kv->name || c.type != DataType::Int32 || !c.device_ptr || n == 0) continue;
+        if (c.name != kv->name || c.type != DataType::Int32 || !c.device_ptr) continue;
         auto it = key_ranges_.find(c.name);
         if (it == key_ranges_.end()) {
           const wdb_col_t col{c.name.c_str(), static_cast<int>(c.type), c.device_ptr, n};
-          double lo = 0, hi = 0;
-          if (wdb_column_minmax(0, nullptr, &col, &lo, &hi)) raise_core();
-          it = key_ranges_.emplace(c.name, std::make_pair(static_cast<long long>(lo), static_cast<long long>(hi))).first;
+          double l = 0, h = 0;
+          if (wdb_column_minmax(0, nullptr, &col, &l, &h)) raise_core();
+          it = key_ranges_.emplace(c.name, std::make_pair(static_cast<long long>(l), static_cast<long long>(h))).first;
         }
-        have_range = true;
-        key_lo = it->second.first;
-        key_hi = it->second.second;
-        expect = std::min<int64_t>(expect, std::max<int64_t>(key_hi - key_lo + 1, 1));
+        *lo = it->second.first;
+        *hi = it->second.second;
+        return true;
       }
+      return false;
+    };
+    if (ast.group_by->keys.size() == 1) {
+      long long lo = 0, hi = -1;
+      if (int_column_range(ast.group_by->keys[0].get(), &lo, &hi)) {
+        have_range = true;
+        key_lo = lo;
+        key_hi = hi;
+      }
+    } else {
+      // Several keys (the reference parses the list, include/expression.hpp:128-130, but reads keys[0] only:
+      // src/warpdb.cpp:362,374).  Integer columns with known ranges fold into ONE composite key
+      //   ((k1 - lo1) * span2 + (k2 - lo2)) * span3 + ...
+      // written with integer literals, so the kernel evaluates it exactly in int arithmetic; its order is
+      // the lexicographic order of (k1, k2, ...), which is the order the groups come back in.
+      if (n == 0) return result;
+      std::string expr;
+      long long total = 1;
+      for (const auto &k : ast.group_by->keys) {
+        long long lo = 0, hi = -1;
+        if (!int_column_range(k.get(), &lo, &hi)) throw std::runtime_error("GROUP BY on several keys needs integer columns");
+        const long long span = hi - lo + 1;
+        if (total > 0x7fffffffll / span) throw std::runtime_error("GROUP BY on several keys: the combined key range exceeds 2^31");
+        total *= span;
+        const std::string term = "(" + k->to_cuda_expr() + " - (" + std::to_string(lo) + "))";
+        expr = expr.empty() ? term : "((" + expr + ") * " + std::to_string(span) + " + " + term + ")";
+      }
+      key = expr;
+      have_range = true;
+      key_lo = 0;
+      key_hi = total - 1;
     }
+    if (have_range) expect = std::min<int64_t>(expect, std::max<int64_t>(key_hi - key_lo + 1, 1));
+    const std::vector<wdb_prune_t> preds = prune_preds(ast.where ? ast.where->get() : nullptr);
     for (int attempt = 0;; ++attempt) {
       wdb_agg_t *t = nullptr;
       if (wdb_agg_create(0, expect, needs, &t)) raise_core();
       std::unique_ptr<wdb_agg_t, int (*)(wdb_agg_t *)> guard(t, wdb_agg_destroy);
       if (have_range && wdb_agg_set_key_range(t, 1, key_lo, key_hi)) raise_core();
-      if (wdb_agg_consume(t, nullptr, dcols.data(), nc, val.c_str(), key.c_str(), cond.c_str(), n, 0)) raise_core();
+      int64_t live = -1;
+      if (wdb_agg_consume_pruned(t, nullptr, dcols.data(), nc, val.c_str(), key.c_str(), cond.c_str(), n, 0, preds.empty() ? nullptr : preds.data(),
+                                 static_cast<int>(preds.size()), &live))
+        raise_core();
+      if (!preds.empty()) {
+        int64_t zr = 0, nz = 0;
+        wdb_zonemap_info(preds[0].zonemap, &zr, &nz);
+        last_zones_live_ = live;
+        last_zones_total_ = nz;
+      }
       if (wdb_agg_size(t, nullptr, &groups)) {
         const std::string msg = wdb_last_error();
         if (msg.find("table overflow") != std::string::npos && attempt < 5) { expect *= 16; continue; }
@@ -431,9 +481,18 @@ std::vector<float> WarpDB::query_sql(const std::string &sql) {
     const int64_t cap = k < 0 ? n : std::min<int64_t>(k, n);
     DeviceBuffer out(sizeof(float) * static_cast<size_t>(std::max<int64_t>(cap, 1)));
     int64_t m = 0;
-    if (wdb_topk(0, nullptr, dcols.data(), nc, ast.order_by->expr->to_cuda_expr().c_str(), sel.c_str(), cond.c_str(),
-                 ast.order_by->ascending ? 0 : 1, k, off, n, out.as<float>(), nullptr, &m))
+    const std::vector<wdb_prune_t> preds = prune_preds(ast.where ? ast.where->get() : nullptr);
+    int64_t live = -1;
+    if (wdb_topk_pruned(0, nullptr, dcols.data(), nc, ast.order_by->expr->to_cuda_expr().c_str(), sel.c_str(), cond.c_str(),
+                        ast.order_by->ascending ? 0 : 1, k, off, n, out.as<float>(), nullptr, &m, preds.empty() ? nullptr : preds.data(),
+                        static_cast<int>(preds.size()), &live))
       raise_core();
+    if (!preds.empty() && live >= 0) {
+      int64_t zr = 0, nz = 0;
+      wdb_zonemap_info(preds[0].zonemap, &zr, &nz);
+      last_zones_live_ = live;
+      last_zones_total_ = nz;
+    }
     return download<float>(out.p, static_cast<size_t>(m));
   }
   // plain SELECT: surviving rows in row order (stable compaction), then OFFSET / LIMIT

@@ -55,6 +55,7 @@ private:
   struct PruneTerm { std::string column; int op; double value; };
   std::vector<PruneTerm> prune_terms(const ASTNode *cond) const;
   void *zonemap_for(const std::string &column);   // wdb_zonemap_t*, nullptr if not prunable
+  std::vector<struct wdb_prune> prune_preds(const ASTNode *cond_ast);
   int filter_project(const std::string &expr, const std::string &cond, const ASTNode *cond_ast, float *d_out, int mode,
                      long long *count);
 

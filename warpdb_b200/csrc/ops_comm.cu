@@ -183,6 +183,15 @@ __global__ void __launch_bounds__(32) topk_merge_kernel(const char *__restrict__
   if (lane == 0) *out_n = found > offset ? found - offset : 0;
 }
 
+int topk_merge_launch(cudaStream_t s, const char *gathered, int nparts, int K, bool desc, int offset, float *out_vals, float *out_keys,
+                      long long *out_n) {
+  if ((size_t)nparts * (size_t)K > 2048) return fail("too many candidate lists for the register top-k merge");
+  topk_merge_kernel<<<1, 32, 0, s>>>(gathered, nparts, K, desc ? 1 : 0, offset, out_vals, out_keys, out_n);
+  stats().launches++;
+  WDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // counts[r] = survivors of rank r (all-gathered) -> out3 = {count of this rank, its global offset, global total}
 __global__ void compact_offsets_kernel(const long long *__restrict__ counts, int nranks, int rank, long long *__restrict__ out3) {
   long long off = 0, tot = 0;
@@ -509,14 +518,11 @@ int wdb_multi_topk(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int ncols
     char *sc;
     if (comm_scratch(c, per_rank * c->nranks + 64, &sc)) return 1;
     long long *d_cnt = (long long *)(sc + per_rank * c->nranks);
-    if ((size_t)c->nranks * (size_t)K > 2048) return fail("too many ranks for the register top-k merge");
     if (topk_candidates(d, s, cols, ncols, order_key(key_expr, descending != 0).c_str(), val_expr, cond, descending != 0, (int)K, n_local, row_base,
                         sc + per_rank * c->rank))
       return 1;
     if (allgather_inplace(c, sc, per_rank, s)) return 1;
-    topk_merge_kernel<<<1, 32, 0, s>>>(sc, c->nranks, (int)K, descending != 0, (int)offset, d_out_vals, d_out_keys, d_cnt);
-    stats().launches++;
-    WDB_CUDA(cudaGetLastError());
+    if (topk_merge_launch(s, sc, c->nranks, (int)K, descending != 0, (int)offset, d_out_vals, d_out_keys, d_cnt)) return 1;
     if (d_n) WDB_CUDA(cudaMemcpyAsync(d_n, d_cnt, 8, cudaMemcpyDeviceToDevice, s));
     if (h_n) {
       long long cnt = 0;

@@ -9,9 +9,11 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <utility>
 #include <vector>
 
-#include "core.hpp"
+#include "agg.hpp"
 
 struct wdb_zonemap {
   wdb::Device *dev = nullptr;
@@ -128,6 +130,63 @@ static int zonemap_launch(wdb_zonemap *z, cudaStream_t s, const void *base, long
   }
   stats().launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// which zones can hold a row passing every predicate -> maximal runs of live zones as row ranges (host);
+// synchronises `s` (the mask is read back: nzones bytes)
+int zone_live_ranges(Device *d, cudaStream_t s, const wdb_prune_t *preds, int npreds, int64_t n, std::vector<std::pair<int64_t, int64_t>> *ranges,
+                     int64_t *live, int64_t *nzones) {
+  if (npreds > kMaxPreds) npreds = kMaxPreds;
+  DevPreds P;
+  P.n = npreds;
+  const wdb_zonemap *z0 = preds[0].zonemap;
+  for (int i = 0; i < npreds; ++i) {
+    const wdb_zonemap *z = preds[i].zonemap;
+    if (!z || z->n != n || z->zshift != z0->zshift) return fail("zone maps must cover the table's %lld rows with one zone size", (long long)n);
+    if (preds[i].op < 0 || preds[i].op > 5) return fail("invalid pruning operator %d", preds[i].op);
+    P.p[i] = DevPred{z->mins, z->maxs, preds[i].op, preds[i].value};
+  }
+  const int64_t nz = z0->nzones;
+  *nzones = nz;
+  *live = 0;
+  ranges->clear();
+  if (nz == 0) return 0;
+  char *buf = nullptr;
+  WDB_CUDA(cudaMallocAsync((void **)&buf, (size_t)nz + 16, s));
+  WDB_CUDA(cudaMemsetAsync(buf, 0, 8, s));
+  zone_mask_kernel<<<(unsigned)std::min<int64_t>((nz + 255) / 256, 4096), 256, 0, s>>>(P, nz, (unsigned char *)(buf + 16), (unsigned long long *)buf);
+  stats().launches++;
+  WDB_CUDA(cudaGetLastError());
+  std::vector<unsigned char> h((size_t)nz);
+  WDB_CUDA(cudaMemcpyAsync(h.data(), buf + 16, (size_t)nz, cudaMemcpyDeviceToHost, s));
+  WDB_CUDA(cudaFreeAsync(buf, s));
+  WDB_CUDA(cudaStreamSynchronize(s));
+  const int64_t zr = 1ll << z0->zshift;
+  for (int64_t z = 0; z < nz;) {
+    if (!h[z]) { ++z; continue; }
+    int64_t e = z;
+    while (e < nz && h[e]) ++e;
+    ranges->push_back({z * zr, std::min<int64_t>(e * zr, n)});
+    *live += e - z;
+    z = e;
+  }
+  return 0;
+}
+int topk_candidates(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncols, const char *key, const char *val, const char *cond,
+                    bool desc, int K, int64_t n, int64_t row_base, char *cand);
+int topk_merge_launch(cudaStream_t s, const char *gathered, int nparts, int K, bool desc, int offset, float *out_vals, float *out_keys,
+                      long long *out_n);
+std::string order_key(const char *key_expr, bool desc);
+
+// columns of the row range [start, end): pointers advanced, lengths cut
+static std::vector<wdb_col_t> slice_cols(const wdb_col_t *cols, int ncols, int64_t start, int64_t end) {
+  std::vector<wdb_col_t> out(cols, cols + ncols);
+  for (auto &c : out) {
+    const size_t sz = (size_t)dtype_size(c.dtype);
+    if (c.dptr && sz) c.dptr = (const char *)c.dptr + (size_t)start * sz;
+    c.len = end - start;
+  }
+  return out;
 }
 
 // pinned staging ring for uploads from pageable host memory: two slots per device, kept across calls
@@ -305,6 +364,69 @@ int wdb_project_filter_pruned(int device, void *stream, const wdb_col_t *cols, i
   } else if (!rc && (h_count || d_count))
     WDB_CUDA(cudaStreamSynchronize(s));
   WDB_CUDA(cudaFreeAsync(buf, s));
+  return rc;
+}
+
+// GROUP BY / ORDER BY ... LIMIT with a WHERE clause over a zone-mapped table: the kernels run on the
+// maximal runs of live zones only (zones are multiples of 2048 rows, so every run keeps the columns'
+// vector alignment).  Worth it when the runs are few and cover under half of the table -- sorted or
+// clustered columns; on a random layout everything is live and the plain call is taken.
+int wdb_agg_consume_pruned(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols, const char *val_expr, const char *key_expr,
+                           const char *cond, int64_t n, int64_t row_base, const wdb_prune_t *preds, int npreds, int64_t *h_zones_live) {
+  if (npreds <= 0 || !preds || !cond || !*cond) return wdb_agg_consume(t, stream, cols, ncols, val_expr, key_expr, cond, n, row_base);
+  if (!t) return fail("null table");
+  Device *d = t->dev;
+  WDB_CUDA(cudaSetDevice(d->id));
+  std::vector<std::pair<int64_t, int64_t>> ranges;
+  int64_t live = 0, nz = 0;
+  if (zone_live_ranges(d, (cudaStream_t)stream, preds, npreds, n, &ranges, &live, &nz)) return 1;
+  if (h_zones_live) *h_zones_live = live;
+  if ((int64_t)ranges.size() > opt("prune.max_ranges", 64) || 2 * live > nz)
+    return wdb_agg_consume(t, stream, cols, ncols, val_expr, key_expr, cond, n, row_base);
+  for (const auto &r : ranges) {
+    const std::vector<wdb_col_t> rc = slice_cols(cols, ncols, r.first, r.second);
+    if (wdb_agg_consume(t, stream, rc.data(), ncols, val_expr, key_expr, cond, r.second - r.first, row_base + r.first)) return 1;
+  }
+  return 0;
+}
+
+int wdb_topk_pruned(int device, void *stream, const wdb_col_t *cols, int ncols, const char *key_expr, const char *val_expr, const char *cond,
+                    int descending, int64_t k, int64_t offset, int64_t n, float *d_out_vals, float *d_out_keys, int64_t *h_n,
+                    const wdb_prune_t *preds, int npreds, int64_t *h_zones_live) {
+  const int64_t K = k + offset;
+  if (npreds <= 0 || !preds || !cond || !*cond || k <= 0 || K > opt("topk.reg_max", 16))
+    return wdb_topk(device, stream, cols, ncols, key_expr, val_expr, cond, descending, k, offset, n, d_out_vals, d_out_keys, h_n);
+  if (!key_expr || !*key_expr) return fail("empty ORDER BY expression");
+  if (!val_expr || !*val_expr) val_expr = key_expr;
+  Device *d;
+  if (get_device(device, &d)) return 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<std::pair<int64_t, int64_t>> ranges;
+  int64_t live = 0, nz = 0;
+  if (zone_live_ranges(d, s, preds, npreds, n, &ranges, &live, &nz)) return 1;
+  if (h_zones_live) *h_zones_live = live;
+  if (ranges.empty() || (int64_t)ranges.size() > std::min<int64_t>(opt("prune.max_ranges", 64), 2048 / K) || 2 * live > nz)
+    return wdb_topk(device, stream, cols, ncols, key_expr, val_expr, cond, descending, k, offset, n, d_out_vals, d_out_keys, h_n);
+  // every run of live zones yields its K best (key, global row) pairs; the one-warp selection of the sharded
+  // ORDER BY merges them (runs are ascending row ranges, so ties keep row order)
+  const size_t per = (size_t)K * 16;
+  char *buf = nullptr;
+  WDB_CUDA(cudaMallocAsync((void **)&buf, per * ranges.size() + 64, s));
+  long long *d_cnt = (long long *)(buf + per * ranges.size());
+  const std::string okey = order_key(key_expr, descending != 0);
+  int rc = 0;
+  for (size_t i = 0; i < ranges.size() && !rc; ++i) {
+    const std::vector<wdb_col_t> cr = slice_cols(cols, ncols, ranges[i].first, ranges[i].second);
+    rc = topk_candidates(d, s, cr.data(), ncols, okey.c_str(), val_expr, cond, descending != 0, (int)K, ranges[i].second - ranges[i].first, ranges[i].first,
+                         buf + per * i);
+  }
+  if (!rc) rc = topk_merge_launch(s, buf, (int)ranges.size(), (int)K, descending != 0, (int)offset, d_out_vals, d_out_keys, d_cnt);
+  long long cnt = 0;
+  if (!rc && h_n) {
+    if (cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) rc = fail("CUDA error: top-k count read-back");
+    *h_n = cnt;
+  }
+  cudaFreeAsync(buf, s);
   return rc;
 }
 }

@@ -107,9 +107,17 @@ class AggTable:
         known = lo is not None and hi is not None
         wc.check(wc.lib().wdb_agg_set_key_range(self.handle, int(known), int(lo) if known else 0, int(hi) if known else -1))
 
-    def consume(self, table, val_expr, key_expr, cond=None, n=None, row_base=0):
+    def consume(self, table, val_expr, key_expr, cond=None, n=None, row_base=0, preds=None):
+        """preds: optional list of (ZoneMap, op, constant) implied by `cond` (zone-map pruning); returns the
+        number of live zones when given."""
         n = num_rows(table) if n is None else n
         cols, nc = wc.make_cols(schema_of(table))
+        if preds:
+            arr = _prune_array(preds)
+            live = C.c_int64(0)
+            wc.check(wc.lib().wdb_agg_consume_pruned(self.handle, _stream(self.device), cols, nc, wc.enc(val_expr), wc.enc(key_expr), wc.enc(cond or ""), n,
+                                                     row_base, arr, len(preds), C.byref(live)))
+            return live.value
         wc.check(wc.lib().wdb_agg_consume(self.handle, _stream(self.device), cols, nc, wc.enc(val_expr), wc.enc(key_expr),
                                           wc.enc(cond or ""), n, row_base))
 
@@ -186,8 +194,18 @@ def group_agg(table, val_expr, key_expr, cond=None, agg=wc.SUM, order=wc.ORDER_K
     return keys[:g.value], vals[:g.value]
 
 
-def topk(table, key_expr, val_expr=None, cond=None, descending=True, k=5, offset=0, want_keys=False):
-    """ORDER BY key_expr [LIMIT k [OFFSET offset]] (k < 0: no limit).  Returns vals (and keys)."""
+def _prune_array(preds):
+    arr = (wc.Prune * max(len(preds), 1))()
+    for i, (zm, op, value) in enumerate(preds):
+        arr[i].zonemap = zm.handle
+        arr[i].op = wc.PRUNE_OPS[op]
+        arr[i].value = float(value)
+    return arr
+
+
+def topk(table, key_expr, val_expr=None, cond=None, descending=True, k=5, offset=0, want_keys=False, preds=None):
+    """ORDER BY key_expr [LIMIT k [OFFSET offset]] (k < 0: no limit).  Returns vals (and keys).
+    preds: optional zone-map pruning terms implied by `cond` (list of (ZoneMap, op, constant))."""
     dev = _dev_index(table)
     n = num_rows(table)
     m = n if k < 0 else min(k, n)
@@ -195,8 +213,12 @@ def topk(table, key_expr, val_expr=None, cond=None, descending=True, k=5, offset
     keys = torch.empty(max(m, 1), dtype=torch.float32, device=f"cuda:{dev}")
     cols, nc = wc.make_cols(schema_of(table))
     cnt = C.c_int64(0)
-    wc.check(wc.lib().wdb_topk(dev, _stream(dev), cols, nc, wc.enc(key_expr), wc.enc(val_expr), wc.enc(cond or ""),
-                               int(descending), k, offset, n, vals.data_ptr(), keys.data_ptr(), C.byref(cnt)))
+    if preds:
+        wc.check(wc.lib().wdb_topk_pruned(dev, _stream(dev), cols, nc, wc.enc(key_expr), wc.enc(val_expr), wc.enc(cond or ""), int(descending), k, offset, n,
+                                          vals.data_ptr(), keys.data_ptr(), C.byref(cnt), _prune_array(preds), len(preds), None))
+    else:
+        wc.check(wc.lib().wdb_topk(dev, _stream(dev), cols, nc, wc.enc(key_expr), wc.enc(val_expr), wc.enc(cond or ""),
+                                   int(descending), k, offset, n, vals.data_ptr(), keys.data_ptr(), C.byref(cnt)))
     if want_keys:
         return vals[:cnt.value], keys[:cnt.value]
     return vals[:cnt.value]
