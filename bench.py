@@ -522,6 +522,11 @@ def ref_nvrtc_projection(table, rows, local):
 
 def run_ours(args):
     import torch
+    # stdout carries exactly ONE line, the JSON: anything libraries print on fd 1 meanwhile (NCCL's version banner
+    # under NCCL_DEBUG, for one) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = dist_setup()
     from warpdb_b200 import _core as wc, ops
     wc.check(wc.lib().wdb_init(local))
@@ -581,6 +586,8 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_baseline_projection(args.cpu_rows)
     if sampler:
         sampler.close()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -63,12 +63,9 @@ def sweep_compact(n):
     out = torch.empty(n, dtype=torch.float32, device="cuda")
     expr, cond = "(price[idx] * 0.9f)", "(price[idx] > 20.0f)"
     cfgs = [{"compact.variant": 3}]
-    # the look-back chain advances one window per L2 round trip: window x slab bytes / RTT bounds the kernel
-    for lb in (1, 2, 4, 8):
-        for slab_m in (4, 8, 2):
-            for mc in (4, 3):
-                if (lb, slab_m, mc) != (1, 4, 4):
-                    cfgs.append({"compact.variant": 3, "compact.lookback": lb, "compact.slab_m": slab_m, "compact.min_ctas": mc})
+    # how much of the parked slab survives until phase 2 depends on the bytes parked at once: CTAs in flight x slab size
+    for mc, slab_m in ((2, 4), (2, 6), (2, 8), (3, 3), (3, 5), (4, 3), (5, 3), (6, 2)):
+        cfgs.append({"compact.variant": 3, "compact.slab_m": slab_m, "compact.min_ctas": mc, "compact.ctas_per_sm": mc})
     best = {}
     for sel in (0.01, 0.5, 0.99):
         price = ops.synth_f32(n, 0xC0FFEE + 3, 0.0, 20.0 / (1.0 - sel))
