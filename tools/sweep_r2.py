@@ -168,8 +168,25 @@ def sweep_group10m(n):
             emit(f, {"G": G, "cfg": cfg, "error": str(e)[:200]})
 
 
+def sweep_topk(n):
+    """fused tail (one launch) vs scan + final + emit (three launches), at shard sizes of 1, 2, 4, 8 GPUs"""
+    f = open(os.path.join(OUT, "r02_sweep_topk.jsonl"), "a")
+    wc.set_udf_source("__device__ float discount(float price, float rate) {\n    return price * rate;\n}\n")
+    for rows in (n // 8, n // 4, n // 2, n):
+        price = ops.synth_f32(rows, 0xC0FFEE + 5, 0.0, 1e6)
+        table = {"price": price}
+        want = torch.topk(price[:1 << 28] * 0.9, 5).values if rows <= 1 << 28 else None
+        for fused in (1, 0):
+            with Opts(**{"topk.fused": fused}):
+                got = ops.topk(table, "discount(price[idx], 0.9f)", None, None, True, 5)
+                ms = time_op(lambda: ops.topk(table, "discount(price[idx], 0.9f)", None, None, True, 5), iters=20)
+            ok = bool(torch.equal(got, torch.topk(torch.cat([torch.topk(price[s:s + (1 << 28)] * 0.9, 5).values for s in range(0, rows, 1 << 28)]), 5).values))
+            emit(f, {"rows": rows, "fused": fused, "ms_incl_host_sync": ms, "gbs": 4.0 * rows / (ms * 1e-3) / 1e9, "frac": 4.0 * rows / (ms * 1e-3) / 1e9 / PEAK, "ok": ok})
+        del price
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 1_000_000_000
     wc.check(wc.lib().wdb_init(0))
-    {"compact": sweep_compact, "group1k": sweep_group1k, "group10m": sweep_group10m}[what](n)
+    {"compact": sweep_compact, "group1k": sweep_group1k, "group10m": sweep_group10m, "topk": sweep_topk}[what](n)

@@ -25,6 +25,19 @@ void set_error(const std::string &msg);
     if (e__ != cudaSuccess) return ::wdb::fail("CUDA error: %s (%s)", cudaGetErrorString(e__), #call); \
   } while (0)
 
+// stream-ordered scratch that is released on every exit path (early error returns included)
+struct Scratch {
+  void *p = nullptr;
+  cudaStream_t s = nullptr;
+  Scratch() = default;
+  Scratch(const Scratch &) = delete;
+  Scratch &operator=(const Scratch &) = delete;
+  ~Scratch() { release(); }
+  cudaError_t alloc(size_t bytes, cudaStream_t stream) { release(); s = stream; return cudaMallocAsync(&p, bytes, stream); }
+  void release() { if (p) { cudaFreeAsync(p, s); p = nullptr; } }
+  template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
 // ---- options / stats ---------------------------------------------------------------------------
 int64_t opt(const char *key, int64_t dflt);
 struct Stats { int64_t compiled = 0, hits = 0, launches = 0; double last_compile_ms = 0; };

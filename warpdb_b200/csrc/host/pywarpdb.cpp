@@ -67,6 +67,17 @@ PYBIND11_MODULE(pywarpdb, m) {
            "query_sql over all GPUs: partial aggregates / top-k candidates are merged GPU to GPU (NCCL).")
       .def_static("query_multi_gpu_csv", &WarpDB::query_multi_gpu_csv, py::arg("csv_path"), py::arg("expr"),
                   py::arg("rows_per_chunk") = 1000000, "Stream a CSV file in chunks across all GPUs and return results.")
+      .def_static("last_csv_stream_stats",
+                  []() {
+                    const WarpDB::CsvStreamStats st = WarpDB::last_csv_stream_stats();
+                    py::dict d;
+                    d["parse_ms"] = st.parse_ms;
+                    d["gpu_ms"] = st.gpu_ms;
+                    d["wall_ms"] = st.wall_ms;
+                    d["chunks"] = st.chunks;
+                    return d;
+                  },
+                  "Where the last query_multi_gpu_csv call spent its time; parse_ms + gpu_ms > wall_ms is the overlap.")
       .def("query_arrow",
            [](WarpDB &db, const std::string &expr, bool shared_memory) {
              auto *arr = new ArrowArray();

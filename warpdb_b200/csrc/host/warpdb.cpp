@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cctype>
+#include <chrono>
 #include <fstream>
 #include <future>
 #include <memory>
@@ -607,7 +608,17 @@ std::vector<float> WarpDB::query_sql_multi_gpu(const std::string &sql) {
   return result;
 }
 
+namespace {
+thread_local WarpDB::CsvStreamStats g_csv_stats;
+double ms_since(std::chrono::steady_clock::time_point t0) {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+}  // namespace
+WarpDB::CsvStreamStats WarpDB::last_csv_stream_stats() { return g_csv_stats; }
+
 std::vector<float> WarpDB::query_multi_gpu_csv(const std::string &csv_path, const std::string &expr, int rows_per_chunk) {
+  const auto t_wall = std::chrono::steady_clock::now();
+  CsvStreamStats st;
   std::ifstream file(csv_path);
   if (!file.is_open()) throw std::runtime_error("Failed to open file: " + csv_path);   // :573-575
   std::string header;
@@ -620,16 +631,28 @@ std::vector<float> WarpDB::query_multi_gpu_csv(const std::string &csv_path, cons
   // parses, uploads, runs and downloads strictly one after the other: src/warpdb.cpp:580-587).
   bool finished = false;
   std::vector<float> all;
-  auto read_chunk = [&]() { return load_csv_chunk(file, rows_per_chunk, finished, names); };
+  double parse_ms = 0;   // only ever touched by the one thread that is parsing at the time
+  auto read_chunk = [&]() {
+    const auto t0 = std::chrono::steady_clock::now();
+    HostTable t = load_csv_chunk(file, rows_per_chunk, finished, names);
+    parse_ms += ms_since(t0);
+    return t;
+  };
   HostTable chunk = read_chunk();
   while (chunk.num_rows() > 0) {
     const bool last = finished;
     std::future<HostTable> next;
     if (!last) next = std::async(std::launch::async, read_chunk);
+    const auto t_gpu = std::chrono::steady_clock::now();
     const std::vector<float> part = run_multi_gpu_jit_host(chunk, p.expr_cuda, p.cond_cuda);
+    st.gpu_ms += ms_since(t_gpu);
+    ++st.chunks;
     all.insert(all.end(), part.begin(), part.end());
     if (last) break;
     chunk = next.get();
   }
+  st.parse_ms = parse_ms;
+  st.wall_ms = ms_since(t_wall);
+  g_csv_stats = st;
   return all;
 }

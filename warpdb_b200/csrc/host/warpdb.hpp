@@ -34,6 +34,11 @@ public:
   std::vector<float> query_sql_multi_gpu(const std::string &sql);
   // stream a CSV in chunks of rows_per_chunk rows through all GPUs
   static std::vector<float> query_multi_gpu_csv(const std::string &csv_path, const std::string &expr, int rows_per_chunk = 1000000);
+  // what the last query_multi_gpu_csv call of this thread spent where: parse_ms (reading + parsing chunks, on
+  // the helper thread), gpu_ms (upload + kernels + download of the chunks), wall_ms; parse_ms + gpu_ms > wall_ms
+  // is the overlap
+  struct CsvStreamStats { double parse_ms = 0, gpu_ms = 0, wall_ms = 0; int chunks = 0; };
+  static CsvStreamStats last_csv_stream_stats();
   // query() exported through the Arrow C data interface
   void query_arrow(const std::string &expr, ArrowArray *out_array, ArrowSchema *out_schema, bool use_shared_memory = false);
 

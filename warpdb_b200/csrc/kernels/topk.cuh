@@ -92,8 +92,35 @@ __device__ __forceinline__ void wdb_block_topk(wdb_list &L, float *__restrict__ 
   }
 }
 
+// the winners' SELECT values: thread i < WDB_K evaluates VAL at row best_r[i] (rows are global ids)
+__device__ __forceinline__ void wdb_topk_emit_rows(const wdb_cols &C, const i64 row_base, const float *best_k, const i64 *best_r, const int offset,
+                                                   float *__restrict__ out_vals, float *__restrict__ out_keys, i64 *__restrict__ out_count) {
+  const int i = threadIdx.x;
+  int valid = 0;
+  if (i < WDB_K) {
+    const i64 r = best_r[i];
+    valid = (r != WDB_ROW_NONE) ? 1 : 0;
+    if (valid && i >= offset) {
+      wdb_rows R;
+      wdb_load_row1(C, r - row_base, R, 0);
+      if (out_vals) out_vals[i - offset] = WDB_VAL(R, 0);
+      if (out_keys) out_keys[i - offset] = best_k[i];
+    }
+  }
+  const int total = __syncthreads_count(valid);
+  if (i == 0) *out_count = total > offset ? total - offset : 0;
+}
+
+// WDB_FUSED_TAIL: the last CTA to finish (a done-counter in global memory) selects among all CTAs' candidates
+// and evaluates the SELECT expression at the winners, so one launch does the work of scan + final + emit:
+// on a 1e9-row shard the two extra launches and their gaps were ~0.1 ms of a 0.7 ms step.
 extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
-wdb_topk_scan(const wdb_cols C, const i64 n, const i64 row_base, float *__restrict__ cand_k, i64 *__restrict__ cand_r) {
+wdb_topk_scan(const wdb_cols C, const i64 n, const i64 row_base, float *__restrict__ cand_k, i64 *__restrict__ cand_r
+#if WDB_FUSED_TAIL
+              , u32 *__restrict__ done, float *__restrict__ best_k, i64 *__restrict__ best_r, const int offset, float *__restrict__ out_vals,
+              float *__restrict__ out_keys, i64 *__restrict__ out_count
+#endif
+) {
   wdb_list L;
   L.clear();
   const i64 nvec = n / WDB_VEC;
@@ -149,6 +176,24 @@ wdb_topk_scan(const wdb_cols C, const i64 n, const i64 row_base, float *__restri
     }
   }
   wdb_block_topk(L, cand_k + (i64)blockIdx.x * WDB_K, cand_r + (i64)blockIdx.x * WDB_K);
+#if WDB_FUSED_TAIL
+  __shared__ u32 s_last;
+  __threadfence();                                  // this CTA's candidates are visible before its ticket is
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(done, 1u) == gridDim.x - 1u) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  L.clear();
+  const i64 m = (i64)gridDim.x * WDB_K;
+  for (i64 i = threadIdx.x; i < m; i += WDB_BLOCK) {
+    const i64 r = __ldcg(cand_r + i);               // written by other SMs: read at the L2
+    if (r != WDB_ROW_NONE) L.offer(__ldcg(cand_k + i), r);
+  }
+  wdb_block_topk(L, best_k, best_r);
+  __syncthreads();
+  wdb_topk_emit_rows(C, row_base, best_k, best_r, offset, out_vals, out_keys, out_count);
+#endif
 }
 
 extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
@@ -167,20 +212,7 @@ wdb_topk_final(const float *__restrict__ cand_k, const i64 *__restrict__ cand_r,
 extern "C" __global__ void wdb_topk_emit(const wdb_cols C, const i64 row_base, const float *__restrict__ best_k,
                                          const i64 *__restrict__ best_r, const int offset, float *__restrict__ out_vals,
                                          float *__restrict__ out_keys, i64 *__restrict__ out_count) {
-  const int i = threadIdx.x;
-  int valid = 0;
-  if (i < WDB_K) {
-    const i64 r = best_r[i];
-    valid = (r != WDB_ROW_NONE) ? 1 : 0;
-    if (valid && i >= offset) {
-      wdb_rows R;
-      wdb_load_row1(C, r - row_base, R, 0);
-      if (out_vals) out_vals[i - offset] = WDB_VAL(R, 0);
-      if (out_keys) out_keys[i - offset] = best_k[i];
-    }
-  }
-  const int total = __syncthreads_count(valid);
-  if (i == 0) *out_count = total > offset ? total - offset : 0;
+  wdb_topk_emit_rows(C, row_base, best_k, best_r, offset, out_vals, out_keys, out_count);
 }
 
 // best key of every tile of WDB_TILE_ROWS rows among rows passing the condition (WDB_KEY_WORST if none)

@@ -144,8 +144,9 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
     const size_t off_bytes = 8 * (size_t)std::max<int64_t>(nchunks, 1), sum_bytes = 8 * (size_t)std::max<int64_t>(nsb, 1);
     const size_t need = 64 + off_bytes + sum_bytes + 4 * (size_t)std::max<int64_t>(nchunks, 1);
     // stream-ordered scratch: concurrent calls on different streams of one device do not share it
-    char *sc = nullptr;
-    WDB_CUDA(cudaMallocAsync((void **)&sc, need, stream));
+    Scratch scratch;
+    WDB_CUDA(scratch.alloc(need, stream));
+    char *sc = scratch.as<char>();
     long long *d_total = (long long *)sc;
     long long *d_offs = (long long *)(sc + 64);
     long long *d_sums = (long long *)(sc + 64 + off_bytes);
@@ -173,7 +174,7 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
     }
     if (d_count) WDB_CUDA(cudaMemcpyAsync(d_count, d_total, 8, cudaMemcpyDeviceToDevice, stream));
     if (h_count) WDB_CUDA(cudaMemcpyAsync(h_count, d_total, 8, cudaMemcpyDeviceToHost, stream));
-    WDB_CUDA(cudaFreeAsync(sc, stream));
+    scratch.release();
     if (h_count) WDB_CUDA(cudaStreamSynchronize(stream));
     return 0;
   }
@@ -187,8 +188,9 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
   // scratch: [0,8) survivor count, [8,12) ticket, [64, 64+8*ntiles) tile status words (+ one word per round of
   // the single-pass variant: at least one slab per CTA and round, so ntiles + 2 words always suffice)
   const size_t need = 64 + (size_t)std::max<int64_t>(ntiles, 1) * 8 + (sp ? (size_t)(ntiles + 2) * 8 : 0);
-  char *sc = nullptr;
-  WDB_CUDA(cudaMallocAsync((void **)&sc, need, stream));
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc(need, stream));
+  char *sc = scratch.as<char>();
   WDB_CUDA(cudaMemsetAsync(sc, 0, need, stream));
   long long *d_cnt = (long long *)sc;
   unsigned *d_ticket = (unsigned *)(sc + 8);
@@ -227,7 +229,7 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
   }
   if (d_count) WDB_CUDA(cudaMemcpyAsync(d_count, d_cnt, 8, cudaMemcpyDeviceToDevice, stream));
   if (h_count) WDB_CUDA(cudaMemcpyAsync(h_count, d_cnt, 8, cudaMemcpyDeviceToHost, stream));
-  WDB_CUDA(cudaFreeAsync(sc, stream));
+  scratch.release();
   if (h_count) WDB_CUDA(cudaStreamSynchronize(stream));
   return 0;
 }

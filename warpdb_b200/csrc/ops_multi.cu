@@ -56,7 +56,12 @@ static int run_shard(ShardJob *job, const wdb_col_t *h_cols, int ncols, const ch
     ring_bytes[job->dev] = need;
   }
   char *pool = ring_ptr[job->dev];
-  std::vector<cudaStream_t> streams(nslots);
+  struct StreamSet {   // destroyed on every exit path
+    std::vector<cudaStream_t> v;
+    ~StreamSet() { for (auto s : v) if (s) cudaStreamDestroy(s); }
+  } stream_set;
+  stream_set.v.assign(nslots, nullptr);
+  std::vector<cudaStream_t> &streams = stream_set.v;
   for (auto &s : streams) WDB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   // carve: per slot, one buffer per used column (256-byte aligned) + the output
   std::vector<std::vector<char *>> in(nslots, std::vector<char *>(used.size()));
@@ -104,7 +109,6 @@ static int run_shard(ShardJob *job, const wdb_col_t *h_cols, int ncols, const ch
   for (auto &s : streams) {
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess && !rc) rc = fail("CUDA error: %s (stream sync)", cudaGetErrorString(e));
-    cudaStreamDestroy(s);
   }
   job->count = written;
   return rc;

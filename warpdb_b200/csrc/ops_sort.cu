@@ -195,6 +195,60 @@ __global__ void gather_f32_kernel(const float *__restrict__ in, const unsigned *
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = in[idx[i]];
 }
 
+// ---- small sorts: one CTA, one launch ---------------------------------------------------------------
+// The callers of jit_sort_float / jit_sort_pairs sort a handful of groups or a LIMITed result
+// (src/warpdb.cpp:370-371,453-455); the radix sort needs 14 launches whatever the size.  Up to 4 096
+// elements: encode, stable bitonic sort of (key << 32 | index) in shared memory, decode, payload
+// permuted alongside -- the index in the low word makes the network stable, like the bubble sorts it replaces.
+constexpr int kSmallSortMax = 4096;
+template <int IS_FLOAT>
+__global__ void __launch_bounds__(1024) small_sort_kernel(void *__restrict__ keys, unsigned *__restrict__ payload, int n, int m, int descending) {
+  extern __shared__ unsigned long long s_comp[];                      // m composites, then n payload words
+  unsigned *s_pay = reinterpret_cast<unsigned *>(s_comp + m);
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    unsigned long long c = ~0ull;                                     // padding sorts last
+    if (i < n) {
+      unsigned k = IS_FLOAT ? f32_to_ordered(reinterpret_cast<const float *>(keys)[i]) : ((unsigned)reinterpret_cast<const int *>(keys)[i] ^ 0x80000000u);
+      if (descending) k = ~k;
+      c = ((unsigned long long)k << 32) | (unsigned)i;
+      if (payload) s_pay[i] = payload[i];
+    }
+    s_comp[i] = c;
+  }
+  __syncthreads();
+  for (int k = 2; k <= m; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int x = i ^ j;
+        if (x > i) {
+          const unsigned long long a = s_comp[i], b = s_comp[x];
+          if ((a > b) == ((i & k) == 0)) { s_comp[i] = b; s_comp[x] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long c = s_comp[i];
+    unsigned k = (unsigned)(c >> 32);
+    if (descending) k = ~k;
+    if (IS_FLOAT) reinterpret_cast<float *>(keys)[i] = ordered_to_f32(k);
+    else reinterpret_cast<int *>(keys)[i] = (int)(k ^ 0x80000000u);
+    if (payload) payload[i] = s_pay[(unsigned)c];
+  }
+}
+// returns true when the small path handled the sort
+static bool small_sort(cudaStream_t s, void *keys, unsigned *payload, long long n, bool is_float, bool ascending) {
+  if (n > opt("sort.small_max", kSmallSortMax) || n > kSmallSortMax) return false;
+  int m = 2;
+  while (m < n) m <<= 1;
+  const size_t smem = (size_t)m * 8 + (payload ? (size_t)n * 4 : 0);
+  const unsigned block = (unsigned)std::min(1024, std::max(32, m / 2));
+  if (is_float) small_sort_kernel<1><<<1, block, smem, s>>>(keys, payload, (int)n, m, ascending ? 0 : 1);
+  else small_sort_kernel<0><<<1, block, smem, s>>>(keys, payload, (int)n, m, ascending ? 0 : 1);
+  stats().launches++;
+  return true;
+}
+
 static unsigned grid_for(Device *d, long long n) {
   return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)d->num_sms * 16));
 }
@@ -242,6 +296,7 @@ template int radix_sort<unsigned long long>(Device *, cudaStream_t, unsigned lon
 // sort floats in place (optionally carrying a float payload that is permuted alongside)
 int sort_f32(Device *d, cudaStream_t s, float *d_keys, float *d_payload, long long n, bool ascending) {
   if (n <= 1) return 0;
+  if (small_sort(s, d_keys, reinterpret_cast<unsigned *>(d_payload), n, true, ascending)) { WDB_CUDA(cudaGetLastError()); return 0; }
   if (d_payload && n >= (1ll << 32)) return fail("ORDER BY with a separate SELECT expression is limited to 2^32 surviving rows (%lld given)", n);
   const size_t nb = sizeof(unsigned) * (size_t)n;
   char *buf = nullptr;
@@ -286,6 +341,7 @@ int wdb_sort_pairs(int device, void *stream, int32_t *d_keys, float *d_vals, int
   if (count <= 1) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const long long n = count;
+  if (small_sort(s, d_keys, reinterpret_cast<unsigned *>(d_vals), n, false, ascending != 0)) { WDB_CUDA(cudaGetLastError()); return 0; }
   const size_t nb = 4 * (size_t)n;
   char *buf = nullptr;
   WDB_CUDA(cudaMallocAsync((void **)&buf, nb * 3, s));

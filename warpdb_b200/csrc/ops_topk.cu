@@ -38,7 +38,7 @@ static int plan_topk(const wdb_col_t *cols, int ncols, const char *key, const ch
   const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)p->vec * 4);
   spec.defines = {{"WDB_VEC", p->vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", opt("topk.ld_hint", 0)}, {"WDB_ST_HINT", 0},
                   {"WDB_BLOCK", p->block}, {"WDB_UNROLL", p->unroll}, {"WDB_K", K}, {"WDB_DESC", desc ? 1 : 0},
-                  {"WDB_HAS_COND", has_cond ? 1 : 0}};
+                  {"WDB_HAS_COND", has_cond ? 1 : 0}, {"WDB_FUSED_TAIL", opt("topk.fused", 1) ? 1 : 0}};
   spec.fns.push_back({"key", "float", key});
   spec.fns.push_back({"val", "float", val});
   if (has_cond) spec.fns.push_back({"cond", "bool", cond});
@@ -75,29 +75,37 @@ static int topk_small(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncol
   const int64_t tile_rows = (int64_t)p.block * p.unroll * p.vec;
   const int64_t ntiles = std::max<int64_t>(1, (n + tile_rows - 1) / tile_rows);
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)d->num_sms * nb);
-  // scratch: candidates of every CTA, the K winners, the count
+  // scratch: candidates of every CTA, the K winners, the count, the done-counter of the fused tail
   const size_t cand = (size_t)grid * K;
   const size_t bytes = cand * 12 + (size_t)K * 12 + 64;
-  char *buf = nullptr;
-  WDB_CUDA(cudaMallocAsync((void **)&buf, bytes, s));
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc(bytes, s));
+  char *buf = scratch.as<char>();
   long long *cand_r = (long long *)buf;
   long long *best_r = cand_r + cand;
   long long *d_cnt = best_r + K;
+  unsigned *d_done = (unsigned *)(d_cnt + 1);
   float *cand_k = (float *)(d_cnt + 2);
   float *best_k = cand_k + cand;
   auto ptrs = col_ptrs(p.spec, cols);
   long long nn = n, rb = 0, m = (long long)cand;
-  {
-    void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r};
+  if (opt("topk.fused", 1)) {   // one launch: the last CTA to finish selects among all candidates and evaluates the SELECT expression
+    WDB_CUDA(cudaMemsetAsync(d_done, 0, 4, s));
+    void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r, &d_done, &best_k, &best_r, &offset, &d_out_vals, &d_out_keys, &d_cnt};
     if (launch(scan, grid, p.block, 0, s, args)) return 1;
-  }
-  {
-    void *args[] = {&cand_k, &cand_r, &m, &best_k, &best_r};
-    if (launch(fin, 1, p.block, 0, s, args)) return 1;
-  }
-  {
-    void *args[] = {ptrs.data(), &rb, &best_k, &best_r, &offset, &d_out_vals, &d_out_keys, &d_cnt};
-    if (launch(emit, 1, 32, 0, s, args)) return 1;
+  } else {
+    {
+      void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r};
+      if (launch(scan, grid, p.block, 0, s, args)) return 1;
+    }
+    {
+      void *args[] = {&cand_k, &cand_r, &m, &best_k, &best_r};
+      if (launch(fin, 1, p.block, 0, s, args)) return 1;
+    }
+    {
+      void *args[] = {ptrs.data(), &rb, &best_k, &best_r, &offset, &d_out_vals, &d_out_keys, &d_cnt};
+      if (launch(emit, 1, 32, 0, s, args)) return 1;
+    }
   }
   long long cnt = 0;
   if (h_n) {
@@ -105,7 +113,6 @@ static int topk_small(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncol
     WDB_CUDA(cudaStreamSynchronize(s));
     *h_n = cnt;
   }
-  WDB_CUDA(cudaFreeAsync(buf, s));
   return 0;
 }
 
@@ -132,29 +139,36 @@ int topk_candidates(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncols,
   const int64_t ntiles = std::max<int64_t>(1, (n + tile_rows - 1) / tile_rows);
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)d->num_sms * nb);
   const size_t ncand = (size_t)grid * K;
-  char *buf = nullptr;
-  WDB_CUDA(cudaMallocAsync((void **)&buf, ncand * 12 + 64, s));
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc(ncand * 12 + 64, s));
+  char *buf = scratch.as<char>();
   long long *cand_r = (long long *)buf;
   long long *d_cnt = cand_r + ncand;
+  unsigned *d_done = (unsigned *)(d_cnt + 1);
   float *cand_k = (float *)(d_cnt + 2);
   float *best_k = (float *)cand, *best_v = best_k + K, *no_keys = nullptr;
   long long *best_r = (long long *)(cand + (size_t)K * 8);
   auto ptrs = col_ptrs(p.spec, cols);
   long long nn = n, rb = row_base, m = (long long)ncand;
   int zero = 0;
-  {
-    void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r};
+  if (opt("topk.fused", 1)) {
+    WDB_CUDA(cudaMemsetAsync(d_done, 0, 4, s));
+    void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r, &d_done, &best_k, &best_r, &zero, &best_v, &no_keys, &d_cnt};
     if (launch(scan, grid, p.block, 0, s, args)) return 1;
+  } else {
+    {
+      void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r};
+      if (launch(scan, grid, p.block, 0, s, args)) return 1;
+    }
+    {
+      void *args[] = {&cand_k, &cand_r, &m, &best_k, &best_r};
+      if (launch(fin, 1, p.block, 0, s, args)) return 1;
+    }
+    {
+      void *args[] = {ptrs.data(), &rb, &best_k, &best_r, &zero, &best_v, &no_keys, &d_cnt};
+      if (launch(emit, 1, 32, 0, s, args)) return 1;
+    }
   }
-  {
-    void *args[] = {&cand_k, &cand_r, &m, &best_k, &best_r};
-    if (launch(fin, 1, p.block, 0, s, args)) return 1;
-  }
-  {
-    void *args[] = {ptrs.data(), &rb, &best_k, &best_r, &zero, &best_v, &no_keys, &d_cnt};
-    if (launch(emit, 1, 32, 0, s, args)) return 1;
-  }
-  WDB_CUDA(cudaFreeAsync(buf, s));
   return 0;
 }
 
@@ -172,8 +186,9 @@ static int topk_large(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncol
     const int64_t tile_rows = (int64_t)p.block * p.unroll * p.vec;
     const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
     if (ntiles >= K) {
-      float *tile_best = nullptr;
-      WDB_CUDA(cudaMallocAsync((void **)&tile_best, sizeof(float) * (size_t)ntiles, s));
+      Scratch tb_scratch;
+      WDB_CUDA(tb_scratch.alloc(sizeof(float) * (size_t)ntiles, s));
+      float *tile_best = tb_scratch.as<float>();
       auto ptrs = col_ptrs(p.spec, cols);
       long long nn = n, nt = ntiles;
       void *args[] = {ptrs.data(), &nn, &tile_best, &nt};
@@ -182,7 +197,6 @@ static int topk_large(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncol
       if (sort_f32(d, s, tile_best, nullptr, ntiles, !desc)) return 1;
       WDB_CUDA(cudaMemcpyAsync(&tau, tile_best + (K - 1), 4, cudaMemcpyDeviceToHost, s));
       WDB_CUDA(cudaStreamSynchronize(s));
-      WDB_CUDA(cudaFreeAsync(tile_best, s));
       // at least K tiles hold a surviving row whose key is at least as good as tau, so the K-th best
       // row passes the test; tau == worst sentinel (fewer than K tiles with survivors) keeps everything
       thresh = desc ? 1 : 2;
@@ -191,14 +205,13 @@ static int topk_large(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncol
   // candidates (value,key) in row order; grow the buffers if the first guess was too small
   int64_t cap = limited ? std::min<int64_t>(n, std::max<int64_t>(1 << 20, 64 * K)) : n;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    float *cv = nullptr, *ck = nullptr;
-    WDB_CUDA(cudaMallocAsync((void **)&cv, sizeof(float) * (size_t)std::max<int64_t>(cap, 1) * 2, s));
-    ck = cv + std::max<int64_t>(cap, 1);
+    Scratch cand_scratch;
+    WDB_CUDA(cand_scratch.alloc(sizeof(float) * (size_t)std::max<int64_t>(cap, 1) * 2, s));
+    float *cv = cand_scratch.as<float>(), *ck = cv + std::max<int64_t>(cap, 1);
     int64_t c = 0;
     const char *cc = (cond && *cond) ? cond : "true";
     if (run_compact_ex(d, s, cols, ncols, val, key, cc, cv, ck, n, nullptr, &c, thresh, tau, cap)) return 1;
     if (c > cap) {  // more candidates than guessed (many ties at the threshold): retry with room for all
-      WDB_CUDA(cudaFreeAsync(cv, s));
       cap = c;
       continue;
     }
@@ -209,7 +222,7 @@ static int topk_large(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncol
       if (d_out_vals) WDB_CUDA(cudaMemcpyAsync(d_out_vals, cv + offset, sizeof(float) * (size_t)m, cudaMemcpyDeviceToDevice, s));
       if (d_out_keys) WDB_CUDA(cudaMemcpyAsync(d_out_keys, ck + offset, sizeof(float) * (size_t)m, cudaMemcpyDeviceToDevice, s));
     }
-    WDB_CUDA(cudaFreeAsync(cv, s));
+    cand_scratch.release();
     if (h_n) { *h_n = m; WDB_CUDA(cudaStreamSynchronize(s)); }
     return 0;
   }
