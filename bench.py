@@ -258,11 +258,19 @@ def run_filter(name, args, rank, world, local, comm, comm1, sampler, peak, peak_
     s = tot / total
     bpr = 4.0 + 4.0 * cnt / max(rows, 1)
     per = ms / args.steps
+    # which kernels the optimizer ran (selectivity feedback from the previous call of this query shape): 5 = staged two-pass
+    # (wdb_count_stage + scan + wdb_gather_stage) for selective filters, 3 = L2-parked slabs (wdb_compact_l2)
+    lv = C.c_int64(0)
+    variant = int(lv.value) if wc.lib().wdb_get_option(b"compact.last_variant", C.byref(lv)) == 0 else 3
+    kernel = "wdb_count_stage" if variant == 5 else "wdb_compact_l2"
     rec = {"query": "SELECT price * 0.9 FROM t WHERE price > 20 (stable compaction)", "baseline_config": "configs[2]", "selectivity": s,
            "rows_total": total, "rows_per_gpu": rows, "scaling": "strong" if world > 1 else "n/a", "ms_per_step": per,
            "value": total / (per * 1e-3), "unit": "rows/s",
-           "roofline": roofline("wdb_compact_l2", name, bpr, rows, ms_local / args.steps, peak, peak_src,
-                                "kernel_ms = the local compaction call (wdb_compact_l2 + its 1-CTA finish kernel) timed with CUDA events"),
+           "roofline": roofline(kernel, name, bpr, rows, ms_local / args.steps, peak, peak_src,
+                                "kernel_ms = the local compaction call timed with CUDA events: " +
+                                ("wdb_count_stage (one streaming pass that parks each chunk's survivors) + group scan + wdb_gather_stage"
+                                 if variant == 5 else "wdb_compact_l2 (one HBM pass, slab re-read from the L2)")),
+           "optimizer": {"compact_variant": variant, "chosen_by": "survivor count of the previous call of this query shape (pinned-slot feedback, no host sync)"},
            "merge_ms": max(per - ms_local / args.steps, 0.0), "collectives": ["ncclAllGather(1 x int64 per rank: survivor counts)"] if world > 1 else [],
            "gpu_launches": launches, "clocks": clocks, "result_checked": ok}
     del price, out

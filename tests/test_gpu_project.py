@@ -166,7 +166,7 @@ def test_kernel_variants_agree(variant, vec, unroll, block):
             wc.set_option(k, None)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_compaction_variants_agree(variant):
     """ticket + register loads / TMA bulk ring / two-pass count-scan-scatter / L2-parked slabs: identical packed output."""
     n = 2_000_003
@@ -180,6 +180,42 @@ def test_compaction_variants_agree(variant):
             assert cnt == len(ref) and np.array_equal(bits(out[:cnt].cpu().numpy()), bits(ref)), (variant, text, where)
     finally:
         wc.set_option("compact.variant", None)
+
+
+@pytest.mark.parametrize("sel", [0.0, 0.004, 0.05, 0.11, 0.13, 0.5, 1.0])
+def test_selective_filters_take_the_staged_kernels_and_stay_exact(sel):
+    """Optimizer: on large tables every call samples the selectivity; the next call of the same query shape reads it and
+    selective filters then run the staged two-pass kernels (variant 5).  (compact.auto = 2 decides on the device
+    instead: both pipelines are launched and the one that is not needed returns at once.)  Their
+    per-chunk slots overflow -- and are recomputed from the input -- when a chunk holds more than 128 survivors
+    (sel ~ 0.11 .. 0.13 straddles that); forced on, they stay exact at any selectivity."""
+    n = 5_000_011
+    hi = 20.0 / (1.0 - sel) if sel < 1.0 else 20.0
+    lo = 0.0 if sel < 1.0 else 21.0
+    t = {"price": orc.synth_f32(n, 31, lo, max(hi, lo + 1.0))}
+    d = dev(t)
+    ref = orc.filter_compact("price * 0.9", "price > 20", t)
+    try:
+        wc.set_option("compact.auto_min_rows", 1 << 20)     # the optimizer's own choice (default: from 2^27 rows on)
+        for mode in (1, 1, 1, 2):     # 1: feedback from the previous call of this query shape (default); 2: selected on the device
+            wc.set_option("compact.auto", mode)
+            out, cnt = ops.project_filter(d, "(price[idx] * 0.9f)", "(price[idx] > 20.0f)", wc.COMPACT)
+            assert cnt == len(ref) and np.array_equal(bits(out[:cnt].cpu().numpy()), bits(ref)), (sel, mode)
+        wc.set_option("compact.auto", None)
+        dcnt = torch.zeros(1, dtype=torch.int64, device="cuda")   # the device-side count of the asynchronous form
+        cols, nc = wc.make_cols(ops.schema_of(d))
+        import ctypes as C
+        wc.check(wc.lib().wdb_project_filter(0, C.c_void_p(torch.cuda.current_stream().cuda_stream), cols, nc, b"(price[idx] * 0.9f)", b"(price[idx] > 20.0f)",
+                                             out.data_ptr(), n, wc.COMPACT, dcnt.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert int(dcnt.item()) == len(ref)
+        wc.set_option("compact.variant", 5)
+        out, cnt = ops.project_filter(d, "(price[idx] * 0.9f)", "(price[idx] > 20.0f)", wc.COMPACT)
+        assert cnt == len(ref) and np.array_equal(bits(out[:cnt].cpu().numpy()), bits(ref)), sel
+    finally:
+        wc.set_option("compact.variant", None)
+        wc.set_option("compact.auto_min_rows", None)
+        wc.set_option("compact.auto", None)
 
 
 def test_compile_error_and_recovery():
@@ -201,7 +237,7 @@ def test_kernel_cache_hits():
     assert s1["launches"] > s0["launches"]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("n", [1, 1023, 8192, 8193, 40_001, 1_000_001])
 def test_no_writes_outside_the_output(variant, n):
     """compute-sanitizer is closed on this pool: guard regions around the output buffer instead.  The

@@ -13,7 +13,8 @@ OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 reports = sys.argv[1:] or ["prof_r02.ncu-rep"]
 # launch order of tools/prof_target_r2.py (two launches per workload; 10 M keys = two index slices per consume)
 ORDER = {"wdb_project": [("projection", 1e9)] * 2,
-         "wdb_compact_l2": [("filter1", 4e9)] * 2 + [("filter50", 4e9)] * 2 + [("filter99", 4e9)] * 2,
+         "wdb_compact_l2": [("filter1", 4e9)] * 1 + [("filter50", 4e9)] * 2 + [("filter99", 4e9)] * 2,
+         "wdb_count_stage": [("filter1", 4e9)] * 2, "wdb_gather_stage": [("filter1", 4e9)] * 2,
          "wdb_group_wp": [("group1k", 2e9)] * 2,
          "wdb_group": [("group10m", 2e9)] * 4,
          "wdb_topk_scan": [("topk5", 8e9)] * 2}
