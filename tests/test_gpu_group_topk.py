@@ -47,9 +47,11 @@ def test_fixture_group_by_kats(fixtures):
     assert k.cpu().tolist() == [5, 4, 3, 2]
 
 
-@pytest.mark.parametrize("groups,n", [(1, 10007), (7, 100003), (1000, 1_000_003), (100_000, 2_000_003), (3_000_000, 4_000_001)])
+@pytest.mark.parametrize("groups,n", [(1, 10007), (7, 100003), (2, 1_100_003), (40, 1_500_007), (110, 1_200_011), (1000, 1_000_003), (100_000, 2_000_003),
+                                      (3_000_000, 4_000_001)])
 @pytest.mark.parametrize("agg", [wc.SUM, wc.AVG, wc.COUNT, wc.MIN, wc.MAX])
 def test_group_by_matches_oracle(groups, n, agg):
+    # 2 / 40 / 110 keys over more than 2^20 rows: the measured key range selects the lane-private accumulators (wdb_group_wp, mode 2)
     t = {"price": orc.synth_f32(n, 21, 0.0, 100.0), "quantity": orc.synth_i32(n, 22, -groups // 2, groups - groups // 2)}
     ref = orc.group_agg("price", "quantity", None, t, agg=agg)
     k, v = ops.group_agg(dev(t), "price[idx]", "quantity[idx]", agg=agg, expected_groups=groups)
@@ -59,6 +61,22 @@ def test_group_by_matches_oracle(groups, n, agg):
         assert np.array_equal(bits(got), bits(ref["vals"]))
     else:
         np.testing.assert_allclose(got, ref["vals"], rtol=SUM_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("groups", [3, 60])
+def test_tiny_key_ranges_first_appearance_order_and_where(groups):
+    """Lane-private accumulators (every lane owns a copy of every accumulator): first-appearance order, WHERE, AVG / MIN."""
+    n = 1_300_021
+    t = {"price": orc.synth_f32(n, 41, -50.0, 50.0), "quantity": orc.synth_i32(n, 42, 5, 5 + groups)}
+    d = dev(t)
+    for agg in (wc.SUM, wc.AVG, wc.MIN, wc.COUNT):
+        ref = orc.group_agg("price", "quantity", "price > 0 - 20", t, agg=agg, order=orc.ORDER_FIRST)
+        k, v = ops.group_agg(d, "price[idx]", "quantity[idx]", cu("price > 0 - 20"), agg=agg, order=wc.ORDER_FIRST, expected_groups=groups)
+        assert np.array_equal(k.cpu().numpy(), ref["keys"]), (groups, agg)
+        if agg in (wc.COUNT, wc.MIN):
+            assert np.array_equal(bits(v.cpu().numpy()), bits(ref["vals"]))
+        else:
+            np.testing.assert_allclose(v.cpu().numpy(), ref["vals"], rtol=SUM_RTOL)
 
 
 def test_group_by_where_expressions_and_unknown_cardinality():

@@ -97,21 +97,13 @@ def group_check(keys, vals, price, qty, G):
 def sweep_group1k(n):
     f = open(os.path.join(OUT, "r02_sweep_group1k.jsonl"), "a")
     price = ops.synth_f32(n, 0xC0FFEE + 4, 0.0, 100.0)
-    for G in (1000, 100, 3000):
+    for G in (2, 10, 50, 100, 200, 1000):
         qty = ops.synth_i32(n, 0xC0FFEE + 104, 0, G)
         table = {"price": price, "quantity": qty}
-        cfgs = []
-        for mode in (0, 1):
-            for warps in (16, 24, 32):
-                for unroll in (1, 2):
-                    for ilp in ((1, 2) if mode == 0 else (1, 2, 4)):
-                        cfgs.append({"group.wp_mode": mode, "group.wp_warps": warps, "group.wp_unroll": unroll, "group.wp_ilp": ilp})
+        cfgs = [{"group.lane_private": 0}, {"group.lane_private": 1}, {"group.lane_private": 1, "group.lane_min_warps": 4},
+                {"group.lane_private": 1, "group.wp_unroll": 1}]
         for agg, needs in ((wc.SUM, wc.NEED_SUM), (wc.AVG, wc.NEED_SUM | wc.NEED_COUNT)):
-            if G != 1000 and agg != wc.SUM:
-                continue
             for cfg in cfgs:
-                if G != 1000 and (cfg["group.wp_unroll"] != 2 or cfg["group.wp_ilp"] != 1):
-                    continue
                 try:
                     with Opts(**cfg):
                         tab = ops.AggTable(0, 1024, needs)

@@ -207,12 +207,15 @@ struct wdb_wp_state {
   u32 sums, mins, maxs, first, tags, cnts;   // byte offsets of this warp's accumulator arrays
   int key_base;
 };
+// accumulator entries per warp: one per id, or -- WDB_WP_MODE == 2, tiny key ranges -- one per (id, lane)
+#define WDB_WP_LANES (WDB_WP_MODE == 2 ? 32 : 1)
+#define WDB_WP_SLOTS (WDB_WP_IDS * WDB_WP_LANES)
 #define WDB_WP_OFF_SUMS 0u
-#define WDB_WP_OFF_MINS (WDB_WP_OFF_SUMS + (WDB_WP_HAS_SUM ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
-#define WDB_WP_OFF_MAXS (WDB_WP_OFF_MINS + (WDB_WP_HAS_MM ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
-#define WDB_WP_OFF_FIRST (WDB_WP_OFF_MAXS + (WDB_WP_HAS_MM ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
-#define WDB_WP_OFF_TAGS (WDB_WP_OFF_FIRST + (WDB_WP_HAS_FIRST ? 8u : 0u) * WDB_WP_IDS * WDB_WP_WARPS)
-#define WDB_WP_OFF_CNTS (WDB_WP_OFF_TAGS + (WDB_WP_MODE == 1 ? 0u : 4u) * WDB_WP_IDS * WDB_WP_WARPS)
+#define WDB_WP_OFF_MINS (WDB_WP_OFF_SUMS + (WDB_WP_HAS_SUM ? 8u : 0u) * WDB_WP_SLOTS * WDB_WP_WARPS)
+#define WDB_WP_OFF_MAXS (WDB_WP_OFF_MINS + (WDB_WP_HAS_MM ? 8u : 0u) * WDB_WP_SLOTS * WDB_WP_WARPS)
+#define WDB_WP_OFF_FIRST (WDB_WP_OFF_MAXS + (WDB_WP_HAS_MM ? 8u : 0u) * WDB_WP_SLOTS * WDB_WP_WARPS)
+#define WDB_WP_OFF_TAGS (WDB_WP_OFF_FIRST + (WDB_WP_HAS_FIRST ? 8u : 0u) * WDB_WP_SLOTS * WDB_WP_WARPS)
+#define WDB_WP_OFF_CNTS (WDB_WP_OFF_TAGS + (WDB_WP_MODE >= 1 ? 0u : 4u) * WDB_WP_SLOTS * WDB_WP_WARPS)
 #define WDB_WP_MIN(W, id) (*reinterpret_cast<i64 *>(wdb_wp_smem + (W).mins + 8u * (id)))
 #define WDB_WP_MAX(W, id) (*reinterpret_cast<i64 *>(wdb_wp_smem + (W).maxs + 8u * (id)))
 #define WDB_WP_FIRST(W, id) (*reinterpret_cast<i64 *>(wdb_wp_smem + (W).first + 8u * (id)))
@@ -333,6 +336,36 @@ __device__ __forceinline__ void wdb_wp_step_match(const wdb_table &T, const wdb_
   }
 }
 #define WDB_WP_STEP wdb_wp_step_match
+#elif WDB_WP_MODE == 2
+// Tiny key ranges (a few dozen ids: GROUP BY status / region / weekday): every LANE owns a private copy of every
+// accumulator, entry id * 32 + lane, i.e. bank = lane -- no bank conflicts, no duplicates to arbitrate, no tags,
+// no votes: a row is one LDS.64 + DADD + STS.64 at two wavefronts each (4 per 32 rows against the 21 of the
+// tag arbitration, which at 10 keys also needs ~4 rounds per step because most lanes collide: 6.1 ms per 1e9 rows).
+template <int NI>
+__device__ __forceinline__ void wdb_wp_step_lane(const wdb_table &T, const wdb_wp_state &W, const u32 lane, const int (&key)[NI],
+                                                 const float (&val)[NI], const bool (&valid)[NI], const i64 row0) {
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const u32 id = (u32)key[i] - (u32)W.key_base;
+    const bool mine = valid[i] && id < (u32)WDB_WP_IDS;
+    if (__any_sync(WDB_FULL_MASK, valid[i] && !mine)) {   // stale statistics: a key outside the promised range
+      if (valid[i] && !mine) wdb_wp_global_row(T, key[i], val[i], row0 + i);
+      __syncwarp();
+    }
+    if (mine) {
+      const u32 s = id * 32u + lane;
+      if (WDB_WP_HAS_SUM) WDB_WP_SUM(W, s) += (double)val[i] + 0.0;
+      if (WDB_WP_HAS_CNT) WDB_WP_CNT(W, s) += 1u;
+      if (WDB_WP_HAS_MM) {
+        const i64 e = wdb_f64_enc((double)val[i]);
+        if (e < WDB_WP_MIN(W, s)) WDB_WP_MIN(W, s) = e;
+        if (e > WDB_WP_MAX(W, s)) WDB_WP_MAX(W, s) = e;
+      }
+      if (WDB_WP_HAS_FIRST && row0 + i < WDB_WP_FIRST(W, s)) WDB_WP_FIRST(W, s) = row0 + i;
+    }
+  }
+}
+#define WDB_WP_STEP wdb_wp_step_lane
 #else
 #define WDB_WP_STEP wdb_wp_step
 #endif
@@ -382,18 +415,18 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
   u32 *all_tags = reinterpret_cast<u32 *>(wdb_wp_smem + WDB_WP_OFF_TAGS);
   u32 *all_cnts = reinterpret_cast<u32 *>(wdb_wp_smem + WDB_WP_OFF_CNTS);
   wdb_wp_state W;
-  W.sums = WDB_WP_OFF_SUMS + 8u * WDB_WP_IDS * warp;
-  W.mins = WDB_WP_OFF_MINS + 8u * WDB_WP_IDS * warp;
-  W.maxs = WDB_WP_OFF_MAXS + 8u * WDB_WP_IDS * warp;
-  W.first = WDB_WP_OFF_FIRST + 8u * WDB_WP_IDS * warp;
-  W.tags = WDB_WP_OFF_TAGS + 4u * WDB_WP_IDS * warp;
-  W.cnts = WDB_WP_OFF_CNTS + 4u * WDB_WP_IDS * warp;
+  W.sums = WDB_WP_OFF_SUMS + 8u * WDB_WP_SLOTS * warp;
+  W.mins = WDB_WP_OFF_MINS + 8u * WDB_WP_SLOTS * warp;
+  W.maxs = WDB_WP_OFF_MAXS + 8u * WDB_WP_SLOTS * warp;
+  W.first = WDB_WP_OFF_FIRST + 8u * WDB_WP_SLOTS * warp;
+  W.tags = WDB_WP_OFF_TAGS + 4u * WDB_WP_SLOTS * warp;
+  W.cnts = WDB_WP_OFF_CNTS + 4u * WDB_WP_SLOTS * warp;
   W.key_base = key_base;
-  for (int s = threadIdx.x; s < WDB_WP_IDS * WDB_WP_WARPS; s += WDB_BLOCK) {
-    if (WDB_WP_HAS_SUM) all_sums[s] = WDB_WP_MODE == 1 ? -0.0 : 0.0;
+  for (int s = threadIdx.x; s < WDB_WP_SLOTS * WDB_WP_WARPS; s += WDB_BLOCK) {
+    if (WDB_WP_HAS_SUM) all_sums[s] = WDB_WP_MODE >= 1 ? -0.0 : 0.0;
     if (WDB_WP_HAS_MM) { all_mins[s] = WDB_ENC_PLUS_INF; all_maxs[s] = WDB_ENC_MINUS_INF; }
     if (WDB_WP_HAS_FIRST) all_first[s] = 0x7fffffffffffffffll;
-    if (WDB_WP_MODE != 1) all_tags[s] = WDB_WP_NOID;
+    if (WDB_WP_MODE == 0) all_tags[s] = WDB_WP_NOID;
     if (WDB_WP_HAS_CNT) all_cnts[s] = 0u;
   }
   __syncthreads();
@@ -439,24 +472,26 @@ wdb_group_wp(const wdb_cols C, const i64 n, const i64 row_base, const wdb_table 
     i64 mn = WDB_ENC_PLUS_INF, mx = WDB_ENC_MINUS_INF, fr = 0x7fffffffffffffffll;
     bool touched = false;
 #pragma unroll 1
-    for (int w = 0; w < WDB_WP_WARPS; ++w) {
-      const int e = w * WDB_WP_IDS + id;
-#if WDB_WP_MODE == 1
-      bool hit;   // every row updates every accumulator the table tracks: any one of them tells
-      if (WDB_WP_HAS_CNT) hit = all_cnts[e] != 0u;
-      else if (WDB_WP_HAS_SUM) hit = (u64)__double_as_longlong(all_sums[e]) != WDB_DENSE_EMPTY;
-      else if (WDB_WP_HAS_MM) hit = all_mins[e] != WDB_ENC_PLUS_INF || all_maxs[e] != WDB_ENC_MINUS_INF;
-      else hit = all_first[e] != 0x7fffffffffffffffll;
-      if (!hit) continue;
+    for (int w = 0; w < WDB_WP_WARPS; ++w)
+#pragma unroll 1
+      for (int l = 0; l < WDB_WP_LANES; ++l) {
+        const int e = w * WDB_WP_SLOTS + (int)id * WDB_WP_LANES + l;
+#if WDB_WP_MODE >= 1
+        bool hit;   // every row updates every accumulator the table tracks: any one of them tells
+        if (WDB_WP_HAS_CNT) hit = all_cnts[e] != 0u;
+        else if (WDB_WP_HAS_SUM) hit = (u64)__double_as_longlong(all_sums[e]) != WDB_DENSE_EMPTY;
+        else if (WDB_WP_HAS_MM) hit = all_mins[e] != WDB_ENC_PLUS_INF || all_maxs[e] != WDB_ENC_MINUS_INF;
+        else hit = all_first[e] != 0x7fffffffffffffffll;
+        if (!hit) continue;
 #else
-      if (all_tags[e] == WDB_WP_NOID) continue;
+        if (all_tags[e] == WDB_WP_NOID) continue;
 #endif
-      touched = true;
-      if (WDB_WP_HAS_SUM) sum += all_sums[w * WDB_WP_IDS + id];
-      if (WDB_WP_HAS_CNT) cnt += all_cnts[w * WDB_WP_IDS + id];
-      if (WDB_WP_HAS_MM) { mn = min(mn, all_mins[w * WDB_WP_IDS + id]); mx = max(mx, all_maxs[w * WDB_WP_IDS + id]); }
-      if (WDB_WP_HAS_FIRST) fr = min(fr, all_first[w * WDB_WP_IDS + id]);
-    }
+        touched = true;
+        if (WDB_WP_HAS_SUM) sum += all_sums[e];
+        if (WDB_WP_HAS_CNT) cnt += all_cnts[e];
+        if (WDB_WP_HAS_MM) { mn = min(mn, all_mins[e]); mx = max(mx, all_maxs[e]); }
+        if (WDB_WP_HAS_FIRST) fr = min(fr, all_first[e]);
+      }
     if (!touched) continue;
     const int key = (int)((u32)key_base + id);
 #if WDB_DENSE

@@ -267,14 +267,23 @@ static unsigned grid_for(Device *d, long long n) {
 }
 
 // warp-private accumulators (wdb_group_wp): bytes per key and whether at least 4 warps per SM fit
-static int64_t wp_bytes_per_id(int needs) {
-  return (opt("group.wp_mode", 0) == 1 ? 0 : 4) + ((needs & WDB_NEED_SUM_BIT) ? 8 : 0) + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0) + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) +
+constexpr int64_t kMaxDynSmem = 232448 - 64;   // sm_100: 227 KB per CTA
+static int64_t wp_acc_bytes(int needs) {   // accumulators of one id (without the arbitration tag)
+  return ((needs & WDB_NEED_SUM_BIT) ? 8 : 0) + ((needs & WDB_NEED_CNT_BIT) ? 4 : 0) + ((needs & WDB_NEED_MINMAX_BIT) ? 16 : 0) +
          ((needs & WDB_NEED_FIRST_BIT) ? 8 : 0);
 }
-constexpr int64_t kMaxDynSmem = 232448 - 64;   // sm_100: 227 KB per CTA
+// Accumulator scheme of the warp-private kernel for a key range of `span` ids:
+//   2  lane-private copies (entry id * 32 + lane: conflict-free, nothing to arbitrate) while at least 8 warps of them fit an SM
+//   0  one copy per warp, duplicates within a warp step arbitrated through a tag array
+//   1  one copy per warp, duplicates found with MATCH.ANY (measured 2.6x slower than 0; kept as an option)
+static int wp_mode_for(int needs, int64_t span) {
+  if (span > 0 && opt("group.lane_private", 1) && kMaxDynSmem / (wp_acc_bytes(needs) * 32 * ((span + 7) / 8 * 8)) >= opt("group.lane_min_warps", 8)) return 2;
+  return (int)opt("group.wp_mode", 0);
+}
+static int64_t wp_bytes_per_id(int needs, int mode) { return mode == 2 ? 32 * wp_acc_bytes(needs) : (mode == 1 ? 0 : 4) + wp_acc_bytes(needs); }
 static bool wp_fits(int needs, int64_t span) {
   if (span <= 0 || span > opt("group.wp_max_span", 4096)) return false;
-  return kMaxDynSmem / (wp_bytes_per_id(needs) * ((span + 7) / 8 * 8)) >= 4;   // fewer warps cannot hide the shared-memory latency
+  return kMaxDynSmem / (wp_bytes_per_id(needs, wp_mode_for(needs, span)) * ((span + 7) / 8 * 8)) >= 4;   // fewer warps cannot hide the shared-memory latency
 }
 
 struct GroupPlan { GenSpec spec; int block, unroll, vec, smem_slots, wp_ids; size_t smem_bytes; const char *entry; };
@@ -300,7 +309,8 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   if (span > 0) expected = std::min(expected, span);          // an integer key cannot form more groups than its range holds
   const int64_t kMaxDyn = kMaxDynSmem;
   int64_t wp = 0;
-  const int64_t wp_per_id = wp_bytes_per_id(needs);
+  const int wp_mode = wp_mode_for(needs, span);
+  const int64_t wp_per_id = wp_bytes_per_id(needs, wp_mode);
   if (use_wp && wp_fits(needs, span)) wp = (span + 7) / 8 * 8;
   int64_t slots = opt("group.smem_slots", -1);
   if (dense && !use_wp) {   // in-range rows go straight to the direct-addressed table: one RED each, nothing to pre-aggregate
@@ -352,7 +362,7 @@ static int plan_group(const wdb_col_t *cols, int ncols, const char *val, const c
   spec.defines = {{"WDB_VEC", p->vec}, {"WDB_ALIGNED", aligned ? 1 : 0}, {"WDB_LD_HINT", ld_hint}, {"WDB_ST_HINT", 0}, {"WDB_DENSE", dense ? 1 : 0},
                   {"WDB_BLOCK", p->block}, {"WDB_UNROLL", p->unroll}, {"WDB_NEEDS", needs}, {"WDB_SMEM_SLOTS", slots},
                   {"WDB_SMEM_LOG2", log2}, {"WDB_SMEM_PROBES", opt("group.smem_probes", 4)}, {"WDB_HAS_COND", has_cond ? 1 : 0},
-                  {"WDB_WP_IDS", wp}, {"WDB_WP_ILP", wp_ilp}, {"WDB_WP_MODE", opt("group.wp_mode", 0)}};
+                  {"WDB_WP_IDS", wp}, {"WDB_WP_ILP", wp_ilp}, {"WDB_WP_MODE", wp > 0 ? wp_mode : 0}};
   spec.fns.push_back({"val", "float", (needs & ~WDB_NEED_CNT_BIT & ~WDB_NEED_FIRST_BIT) ? val : "0.0f"});  // COUNT never evaluates its argument (src/warpdb.cpp:376)
   spec.fns.push_back({"key", "int", key});
   if (has_cond) spec.fns.push_back({"cond", "bool", cond});
