@@ -97,7 +97,8 @@ static unsigned long long *sel_feedback_slot(Device *d, size_t key) {
 struct CompactPlan { GenSpec spec; int block, unroll, vec, variant, stage_cap, stage_m; int64_t tile_rows; bool two; size_t smem; };
 
 static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, const char *expr2, const char *cond,
-                        bool check_alignment, int thresh, CompactPlan *p, bool prune = false, int force_variant = -1, bool auto_sel = false) {
+                        bool check_alignment, int thresh, CompactPlan *p, bool prune = false, int force_variant = -1, bool auto_sel = false,
+                        int stage_cap_hint = 0) {
   GenSpec &spec = p->spec;
   spec.kind = "compact";
   if (!cond || !*cond) cond = "true";
@@ -115,7 +116,9 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
   if (unroll < 1 || unroll > 8) return fail("compact.unroll must be in [1,8]");
   const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)vec * 4);
   if (!aligned && variant == 1) variant = 2;       // bulk copies need 16-byte aligned columns
-  const int stage_cap = (int)opt("compact.stage_cap", 128);
+  // slot of a chunk's parked survivors: the smaller it is, the closer the slots lie in DRAM for the gather pass
+  // (the optimizer sizes it from the selectivity it has seen: 4 x the expected survivors per chunk + 16, 32 ... 128)
+  const int stage_cap = (int)opt("compact.stage_cap", stage_cap_hint > 0 ? stage_cap_hint : 128);
   // chunks per warp: 1 is fastest when the kernels run (profiles/r02_sweep_compact_staged.jsonl); the device-selected
   // twin pipelines use 8 so that the pipeline that is not needed costs few CTA launches
   const int stage_m = (int)std::max<int64_t>(1, std::min<int64_t>(32, opt("compact.stage_m", auto_sel ? 8 : 1)));
@@ -309,6 +312,7 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
   const int64_t auto_mode = (!two_out && !zmask && opt("compact.variant", -1) < 0 && n >= opt("compact.auto_min_rows", 1 << 27)) ? opt("compact.auto", 1) : 0;
   int force = -1;
   unsigned long long *fb_slot = nullptr;
+  int cap_hint = 0;
   if (auto_mode == 1) {
     // Optimizer (default): selective filters (selectivity below compact.stage_max_sel_permille) run the staged
     // two-pass kernels, everything else the L2-parked slabs.  The statistic is the query's own result: every call
@@ -321,7 +325,11 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
       fb_slot = sel_feedback_slot(d, std::hash<std::string>{}(gen_source(p5.spec)) ^ (std::hash<long long>{}((long long)n) * 0x9E3779B97F4A7C15ull));
       if (fb_slot) {
         const unsigned long long survivors = *(volatile unsigned long long *)fb_slot;
-        if (survivors != ~0ull && survivors * 1000ull <= (unsigned long long)n * (unsigned long long)opt("compact.stage_max_sel_permille", 45)) force = 5;
+        if (survivors != ~0ull && survivors * 1000ull <= (unsigned long long)n * (unsigned long long)opt("compact.stage_max_sel_permille", 45)) {
+          force = 5;
+          const double per_chunk = (double)survivors / (double)n * (double)(p5.tile_rows / (p5.block / 32));
+          cap_hint = per_chunk * 4.0 + 16.0 <= 32.0 ? 32 : (per_chunk * 4.0 + 16.0 <= 64.0 ? 64 : 128);
+        }
       }
     }
   }
@@ -360,7 +368,7 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
   }
   if (!cnt) {
     CompactPlan p;
-    if (plan_compact(cols, ncols, expr, expr2, cond, true, thresh, &p, zmask != nullptr, force)) return 1;
+    if (plan_compact(cols, ncols, expr, expr2, cond, true, thresh, &p, zmask != nullptr, force, false, cap_hint)) return 1;
     if (check_zones(p)) return 1;
     if (!two_out) wdb_set_option("compact.last_variant", p.variant);   // introspection (bench.py labels its roofline with it)
     if (launch_compact_plan(d, stream, p, cols, d_out, d_out2, n, tau, out_cap, zmask, zshift, nullptr, sa, &cnt)) return 1;
