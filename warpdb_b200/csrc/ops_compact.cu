@@ -1,5 +1,6 @@
 // ops_compact.cu -- host side of the single-pass stable compaction (kernels/compact.cuh).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -117,7 +118,8 @@ static int plan_compact(const wdb_col_t *cols, int ncols, const char *expr, cons
   const bool aligned = !check_alignment || all_aligned(spec.used, cols, nullptr, (size_t)vec * 4);
   if (!aligned && variant == 1) variant = 2;       // bulk copies need 16-byte aligned columns
   // slot of a chunk's parked survivors: the smaller it is, the closer the slots lie in DRAM for the gather pass
-  // (the optimizer sizes it from the selectivity it has seen: 4 x the expected survivors per chunk + 16, 32 ... 128)
+  // (the optimizer sizes it from the selectivity it has seen: expected survivors per chunk + 6 sigma, 32 / 64 / 128;
+  // a chunk that overflows its slot anyway is recomputed from the input by the gather pass)
   const int stage_cap = (int)opt("compact.stage_cap", stage_cap_hint > 0 ? stage_cap_hint : 128);
   // chunks per warp: 1 is fastest when the kernels run (profiles/r02_sweep_compact_staged.jsonl); the device-selected
   // twin pipelines use 8 so that the pipeline that is not needed costs few CTA launches
@@ -328,7 +330,8 @@ int run_compact_ex(Device *d, cudaStream_t stream, const wdb_col_t *cols, int nc
         if (survivors != ~0ull && survivors * 1000ull <= (unsigned long long)n * (unsigned long long)opt("compact.stage_max_sel_permille", 45)) {
           force = 5;
           const double per_chunk = (double)survivors / (double)n * (double)(p5.tile_rows / (p5.block / 32));
-          cap_hint = per_chunk * 4.0 + 16.0 <= 32.0 ? 32 : (per_chunk * 4.0 + 16.0 <= 64.0 ? 64 : 128);
+          const double need = per_chunk + 6.0 * std::sqrt(per_chunk) + 2.0;   // mean + 6 sigma of the (binomial) survivors per chunk
+          cap_hint = need <= 32.0 ? 32 : (need <= 64.0 ? 64 : 128);
         }
       }
     }
