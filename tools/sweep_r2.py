@@ -165,12 +165,12 @@ def sweep_topk(n):
         price = ops.synth_f32(rows, 0xC0FFEE + 5, 0.0, 1e6)
         table = {"price": price}
         want = torch.topk(price[:1 << 28] * 0.9, 5).values if rows <= 1 << 28 else None
-        for fused in (1, 0):
-            with Opts(**{"topk.fused": fused}):
+        for fused, waves in ((1, 1), (1, 2)):
+            with Opts(**{"topk.fused": fused, "topk.waves": waves}):
                 got = ops.topk(table, "discount(price[idx], 0.9f)", None, None, True, 5)
                 ms = time_op(lambda: ops.topk(table, "discount(price[idx], 0.9f)", None, None, True, 5), iters=20)
             ok = bool(torch.equal(got, torch.topk(torch.cat([torch.topk(price[s:s + (1 << 28)] * 0.9, 5).values for s in range(0, rows, 1 << 28)]), 5).values))
-            emit(f, {"rows": rows, "fused": fused, "ms_incl_host_sync": ms, "gbs": 4.0 * rows / (ms * 1e-3) / 1e9, "frac": 4.0 * rows / (ms * 1e-3) / 1e9 / PEAK, "ok": ok})
+            emit(f, {"rows": rows, "fused": fused, "waves": waves, "ms_incl_host_sync": ms, "gbs": 4.0 * rows / (ms * 1e-3) / 1e9, "frac": 4.0 * rows / (ms * 1e-3) / 1e9 / PEAK, "ok": ok})
         del price
 
 

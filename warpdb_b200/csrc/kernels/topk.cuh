@@ -115,7 +115,8 @@ __device__ __forceinline__ void wdb_topk_emit_rows(const wdb_cols &C, const i64 
 // and evaluates the SELECT expression at the winners, so one launch does the work of scan + final + emit:
 // on a 1e9-row shard the two extra launches and their gaps were ~0.1 ms of a 0.7 ms step.
 extern "C" __global__ void __launch_bounds__(WDB_BLOCK)
-wdb_topk_scan(const wdb_cols C, const i64 n, const i64 row_base, float *__restrict__ cand_k, i64 *__restrict__ cand_r
+wdb_topk_scan(const wdb_cols C, const i64 n, const i64 row_base, float *__restrict__ cand_k, i64 *__restrict__ cand_r,
+              const float *__restrict__ tau0   // optional: the K-th best key of a sample of the rows (a pre-pass of this kernel)
 #if WDB_FUSED_TAIL
               , u32 *__restrict__ done, float *__restrict__ best_k, i64 *__restrict__ best_r, const int offset, float *__restrict__ out_vals,
               float *__restrict__ out_keys, i64 *__restrict__ out_count
@@ -123,6 +124,9 @@ wdb_topk_scan(const wdb_cols C, const i64 n, const i64 row_base, float *__restri
 ) {
   wdb_list L;
   L.clear();
+  // warp-uniform threshold: no row worse than it can reach the result.  It starts from the K-th best key of a sample
+  // (K rows beat it already; the host runs this kernel over the first 2^20 rows first) and tightens with the lanes' lists.
+  float tau = tau0 ? __ldg(tau0) : WDB_KEY_WORST;
   const i64 nvec = n / WDB_VEC;
   const i64 tile_vecs = (i64)WDB_BLOCK * WDB_UNROLL;
   const i64 ntiles = (nvec + tile_vecs - 1) / tile_vecs;
@@ -135,7 +139,7 @@ wdb_topk_scan(const wdb_cols C, const i64 n, const i64 row_base, float *__restri
       if (full || v0 + (i64)u * WDB_BLOCK < nvec) wdb_load_rows(C, (v0 + (i64)u * WDB_BLOCK) * WDB_VEC, R[u]);
 #pragma unroll
     for (int u = 0; u < WDB_UNROLL; ++u) {
-      if (!(full || v0 + (i64)u * WDB_BLOCK < nvec)) continue;
+      const bool have = full || v0 + (i64)u * WDB_BLOCK < nvec;       // warp-uniform except in the last tile
       const i64 row = (v0 + (i64)u * WDB_BLOCK) * WDB_VEC;
       // Evaluate the whole vector, then test its best key against this thread's current worst
       // once: after the first few tiles almost every vector is rejected by that single compare,
@@ -143,25 +147,50 @@ wdb_topk_scan(const wdb_cols C, const i64 n, const i64 row_base, float *__restri
       // ~20 instructions per row to remain HBM-bound at 4 B/row).
       float key[WDB_VEC];
       float vbest = WDB_KEY_WORST;
+      if (have) {
 #pragma unroll
-      for (int j = 0; j < WDB_VEC; ++j) {
-        key[j] = WDB_KEY(R[u], j);
+        for (int j = 0; j < WDB_VEC; ++j) {
+          key[j] = WDB_KEY(R[u], j);
 #if WDB_HAS_COND
-        if (!WDB_COND(R[u], j)) key[j] = __int_as_float(0x7fc00000);   // NaN: never better than anything
+          if (!WDB_COND(R[u], j)) key[j] = __int_as_float(0x7fc00000);   // NaN: never better than anything
 #endif
 #if WDB_DESC
-        vbest = fmaxf(vbest, key[j]);
+          vbest = fmaxf(vbest, key[j]);
 #else
-        vbest = fminf(vbest, key[j]);
+          vbest = fminf(vbest, key[j]);
+#endif
+        }
+      }
+      // A row below the K-th best key of ANY lane of the warp cannot reach the result (K rows beat it already), so the
+      // vector is tested against the best of the lanes' K-th keys (tau), not only against this thread's own list: a
+      // thread sees too few rows to build a sharp threshold of its own (6 600 on a 1e9-row shard), and whenever
+      // one lane of a warp passes the test the whole warp walks the insertion code -- with private thresholds that
+      // was still every fifth vector at the end of such a shard (0.73 ms where 0.61 ms is the roofline).
+#if WDB_DESC
+      const bool pass = have && vbest >= fmaxf(L.k[WDB_K - 1], tau);
+#else
+      const bool pass = have && vbest <= fminf(L.k[WDB_K - 1], tau);
+#endif
+      if (!__any_sync(WDB_FULL_MASK, pass)) continue;                 // warp-uniform
+      if (pass) {
+#pragma unroll
+        for (int j = 0; j < WDB_VEC; ++j) L.offer(key[j], row_base + row + j);
+      }
+      float b = L.k[WDB_K - 1];                                       // lists changed: refresh the warp's threshold
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(WDB_FULL_MASK, b, o);
+#if WDB_DESC
+        b = fmaxf(b, ob);
+#else
+        b = fminf(b, ob);
 #endif
       }
 #if WDB_DESC
-      if (!(vbest >= L.k[WDB_K - 1])) continue;
+      tau = fmaxf(tau, b);
 #else
-      if (!(vbest <= L.k[WDB_K - 1])) continue;
+      tau = fminf(tau, b);
 #endif
-#pragma unroll
-      for (int j = 0; j < WDB_VEC; ++j) L.offer(key[j], row_base + row + j);
     }
   }
   if (blockIdx.x == 0) {

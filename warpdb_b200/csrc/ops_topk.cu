@@ -60,6 +60,34 @@ static std::vector<const void *> col_ptrs(const GenSpec &spec, const wdb_col_t *
   return ptrs;
 }
 
+// Pre-pass of the register top-k: the same kernel over the first 2^20 rows with a handful of CTAs.  The K-th best key
+// of that sample is a valid threshold for the whole column (K rows beat it already), so the main pass starts with a
+// sharp test instead of warming up ~150 K cold per-thread lists.  `slot` (>= 12 K + 64 bytes of the call's scratch)
+// receives the sample's winners; *tau0 points at its K-th key.  Skipped for small inputs.
+static int topk_sample_threshold(Device *d, cudaStream_t s, const Kernel &scan, const TopkPlan &p, std::vector<const void *> &ptrs, int64_t n,
+                                 int64_t row_base, int K, char *slot, float *cand_k, long long *cand_r, const float **tau0) {
+  *tau0 = nullptr;
+  const int64_t sample = opt("topk.sample_rows", 1 << 20);
+  if (sample <= 0 || n < opt("topk.sample_min_rows", 1 << 26)) return 0;
+  slot = (char *)(((uintptr_t)slot + 15) & ~(uintptr_t)15);
+  long long *s_r = (long long *)slot;
+  long long *s_cnt = s_r + K;
+  unsigned *s_done = (unsigned *)(s_cnt + 1);
+  float *s_k = (float *)(s_cnt + 2);
+  long long nn = std::min<int64_t>(sample, n), rb = row_base;
+  const int64_t tile_rows = (int64_t)p.block * p.unroll * p.vec;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((nn + tile_rows - 1) / tile_rows, d->num_sms));
+  int zero = 0;
+  float *no_f = nullptr;
+  const float *no_tau = nullptr;
+  WDB_CUDA(cudaMemsetAsync(s_done, 0, 4, s));
+  // the candidates of this pre-pass land in the head of the main pass's candidate arrays, which the main pass rewrites
+  void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r, &no_tau, &s_done, &s_k, &s_r, &zero, &no_f, &no_f, &s_cnt};
+  if (launch(scan, grid, p.block, 0, s, args)) return 1;
+  *tau0 = s_k + (K - 1);
+  return 0;
+}
+
 static int topk_small(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncols, const char *key, const char *val, const char *cond,
                       bool desc, int K, int offset, int64_t n, float *d_out_vals, float *d_out_keys, int64_t *h_n) {
   TopkPlan p;
@@ -74,10 +102,11 @@ static int topk_small(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncol
   nb = std::max(1, std::min<int>(nb, (int)opt("topk.ctas_per_sm", 8)));
   const int64_t tile_rows = (int64_t)p.block * p.unroll * p.vec;
   const int64_t ntiles = std::max<int64_t>(1, (n + tile_rows - 1) / tile_rows);
-  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)d->num_sms * nb);
-  // scratch: candidates of every CTA, the K winners, the count, the done-counter of the fused tail
+  // a few waves of CTAs instead of one persistent wave: the hardware scheduler evens out the CTAs' finishing times
+  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)d->num_sms * nb * std::max<int64_t>(1, opt("topk.waves", 1)));
+  // scratch: candidates of every CTA, the K winners, the count, the done-counter of the fused tail, the pre-pass's winners
   const size_t cand = (size_t)grid * K;
-  const size_t bytes = cand * 12 + (size_t)K * 12 + 64;
+  const size_t bytes = cand * 12 + (size_t)K * 12 + 64 + (size_t)K * 12 + 64;
   Scratch scratch;
   WDB_CUDA(scratch.alloc(bytes, s));
   char *buf = scratch.as<char>();
@@ -89,13 +118,15 @@ static int topk_small(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncol
   float *best_k = cand_k + cand;
   auto ptrs = col_ptrs(p.spec, cols);
   long long nn = n, rb = 0, m = (long long)cand;
+  const float *tau0 = nullptr;
   if (opt("topk.fused", 1)) {   // one launch: the last CTA to finish selects among all candidates and evaluates the SELECT expression
+    if (topk_sample_threshold(d, s, scan, p, ptrs, n, 0, K, (char *)(best_k + K), cand_k, cand_r, &tau0)) return 1;
     WDB_CUDA(cudaMemsetAsync(d_done, 0, 4, s));
-    void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r, &d_done, &best_k, &best_r, &offset, &d_out_vals, &d_out_keys, &d_cnt};
+    void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r, &tau0, &d_done, &best_k, &best_r, &offset, &d_out_vals, &d_out_keys, &d_cnt};
     if (launch(scan, grid, p.block, 0, s, args)) return 1;
   } else {
     {
-      void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r};
+      void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r, &tau0};
       if (launch(scan, grid, p.block, 0, s, args)) return 1;
     }
     {
@@ -137,10 +168,11 @@ int topk_candidates(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncols,
   nb = std::max(1, std::min<int>(nb, (int)opt("topk.ctas_per_sm", 8)));
   const int64_t tile_rows = (int64_t)p.block * p.unroll * p.vec;
   const int64_t ntiles = std::max<int64_t>(1, (n + tile_rows - 1) / tile_rows);
-  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)d->num_sms * nb);
+  // a few waves of CTAs instead of one persistent wave: the hardware scheduler evens out the CTAs' finishing times
+  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)d->num_sms * nb * std::max<int64_t>(1, opt("topk.waves", 1)));
   const size_t ncand = (size_t)grid * K;
   Scratch scratch;
-  WDB_CUDA(scratch.alloc(ncand * 12 + 64, s));
+  WDB_CUDA(scratch.alloc(ncand * 12 + 64 + (size_t)K * 12 + 64, s));
   char *buf = scratch.as<char>();
   long long *cand_r = (long long *)buf;
   long long *d_cnt = cand_r + ncand;
@@ -151,13 +183,15 @@ int topk_candidates(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncols,
   auto ptrs = col_ptrs(p.spec, cols);
   long long nn = n, rb = row_base, m = (long long)ncand;
   int zero = 0;
+  const float *tau0 = nullptr;
   if (opt("topk.fused", 1)) {
+    if (topk_sample_threshold(d, s, scan, p, ptrs, n, row_base, K, (char *)(cand_k + ncand), cand_k, cand_r, &tau0)) return 1;
     WDB_CUDA(cudaMemsetAsync(d_done, 0, 4, s));
-    void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r, &d_done, &best_k, &best_r, &zero, &best_v, &no_keys, &d_cnt};
+    void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r, &tau0, &d_done, &best_k, &best_r, &zero, &best_v, &no_keys, &d_cnt};
     if (launch(scan, grid, p.block, 0, s, args)) return 1;
   } else {
     {
-      void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r};
+      void *args[] = {ptrs.data(), &nn, &rb, &cand_k, &cand_r, &tau0};
       if (launch(scan, grid, p.block, 0, s, args)) return 1;
     }
     {
