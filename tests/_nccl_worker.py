@@ -70,6 +70,15 @@ def main():
     keys, vals = comm.group_agg(table, "price[idx]", "(quantity[idx] * 1301)", "(price[idx] > 20.0f)", wc.AVG, wc.ORDER_KEY_DESC, row_base=s)
     assert np.array_equal(keys.cpu().numpy(), r["keys"])
     np.testing.assert_allclose(vals.cpu().numpy(), r["vals"], rtol=1e-6)
+    # the same with the table filled in three index slices: the all-reduce of a finished slice runs on a side stream
+    # while the next slice's kernel runs (the 10 M-key configuration of the benchmark takes this path with two slices)
+    wc.set_option("group.dense_passes", 3)
+    for agg in (wc.AVG, wc.MAX):
+        r = orc.group_agg("price", "quantity * 1301", "price > 20", full, agg=agg)
+        keys, vals = comm.group_agg(table, "price[idx]", "(quantity[idx] * 1301)", "(price[idx] > 20.0f)", agg, wc.ORDER_KEY_ASC, row_base=s)
+        assert np.array_equal(keys.cpu().numpy(), r["keys"]), agg
+        np.testing.assert_allclose(vals.cpu().numpy(), r["vals"], rtol=1e-6)
+    wc.set_option("group.dense_passes", None)
     for agg in (wc.MIN, wc.MAX, wc.COUNT):
         r = orc.group_agg("price", "quantity", "price > 20", full, agg=agg)
         keys, vals = comm.group_agg(table, "price[idx]", "quantity[idx]", "(price[idx] > 20.0f)", agg, wc.ORDER_KEY_ASC, row_base=s, key_range=(-50, 1949))

@@ -23,6 +23,9 @@ JOBS = [
     ("wdb_project", "project", "((price[idx] * quantity[idx]) * 1.08f)", None, None, wc.DENSE, {}, "wdb_project"),
     ("wdb_compact_l2", "compact", "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", 0, {}, "wdb_compact_l2"),
     ("wdb_compact_sp", "compact", "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", 0, {"compact.variant": 4}, "wdb_compact_sp"),
+    ("wdb_count_stage", "compact", "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", 0, {"compact.variant": 5}, "wdb_count_stage"),
+    ("wdb_gather_stage", "compact", "(price[idx] * 0.9f)", None, "(price[idx] > 20.0f)", 0, {"compact.variant": 5}, "wdb_gather_stage"),
+    ("wdb_group_wp_lane_private", "group", "price[idx]", "quantity[idx]", None, wc.SUM, {"group.debug_span": 10}, "wdb_group_wp"),
     ("wdb_group_wp", "group", "price[idx]", "quantity[idx]", None, wc.SUM, {"group.debug_span": 1000}, "wdb_group_wp"),
     ("wdb_group_dense", "group", "price[idx]", "quantity[idx]", None, wc.SUM, {"group.debug_span": 10_000_000}, "wdb_group"),
     ("wdb_group_hash", "group", "price[idx]", "quantity[idx]", None, wc.SUM, {}, "wdb_group"),

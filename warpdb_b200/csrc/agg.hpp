@@ -1,6 +1,8 @@
 // agg.hpp -- the aggregation-table object behind wdb_agg_t, shared by ops_group.cu (consume / merge /
 // export) and ops_comm.cu (cross-GPU merge of partial aggregates).  Internal, not part of the C ABI.
 #pragma once
+#include <functional>
+
 #include "core.hpp"
 #include "kernels/group_table.cuh"
 
@@ -16,6 +18,10 @@ struct wdb_agg {
   bool dense_live = false;  // holds aggregates (T.dspan > 0)
   bool have_range = false;  // optimizer statistics: every key of the next consume calls lies in [key_lo, key_hi]
   int64_t key_lo = 0, key_hi = -1;
+  // cross-GPU merge overlapped with the aggregation: called by wdb_agg_consume after it has launched the kernel of
+  // index slice [lo, hi) of the direct-addressed table (ops_comm.cu all-reduces that slice on a side stream while the
+  // next slice's kernel runs)
+  std::function<int(unsigned lo, unsigned hi)> after_slice;
 };
 
 namespace wdb {

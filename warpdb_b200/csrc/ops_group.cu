@@ -681,6 +681,7 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
       unsigned lo = (unsigned)(i * slice), hi = (unsigned)std::min<int64_t>((i + 1) * slice, (int64_t)t->T.dspan);
       void *args[] = {ptrs.data(), &nn, &rb, &t->T, &lo, &hi};
       if (launch(k, grid, p.block, p.smem_bytes, (cudaStream_t)stream, args)) return 1;
+      if (t->after_slice && t->after_slice(lo, hi)) return 1;
     }
     return 0;
   }
