@@ -338,7 +338,8 @@ def run_group(name, args, rank, world, local, comm, comm1, sampler, peak, peak_s
            "value": total / (per * 1e-3), "unit": "rows/s",
            "roofline": roofline(kernel, name, 8.0, rows, kernel_ms, peak, peak_src, "kernel_ms = the consume launch(es) alone; the step adds table reset, all-reduce and ordered export"),
            "local_ms": ms_local / args.steps, "merge_ms": max(per - ms_local / args.steps, 0.0),
-           "collectives": [f"ncclAllReduce(sum, float64 x {rng[1] - rng[0] + 1}: direct-addressed partial sums)"] if world > 1 else [],
+           "collectives": [f"ncclAllReduce(sum, float64 x {rng[1] - rng[0] + 1}: direct-addressed partial sums" +
+                           ("; per index slice of the table on a side stream, overlapped with the next slice's kernel)" if G > 4096 else ")")] if world > 1 else [],
            "merge_bytes_per_gpu": 8 * (rng[1] - rng[0] + 1) if world > 1 else 0,
            "gpu_launches": launches, "clocks": clocks, "result_checked": ok}
     del price, qty, ref
@@ -378,7 +379,8 @@ def run_topk(name, args, rank, world, local, comm, comm1, sampler, peak, peak_sr
            "rows_total": total, "rows_per_gpu": rows, "scaling": "strong" if world > 1 else "n/a", "ms_per_step": per,
            "value": total / (per * 1e-3), "unit": "rows/s",
            "roofline": roofline("wdb_topk_scan", name, 4.0, rows, ms_local / args.steps, peak, peak_src,
-                                "kernel_ms = the local step (wdb_topk_scan + the 1-CTA final and emit kernels, ~15 us) timed with CUDA events"),
+                                "kernel_ms = the local step timed with CUDA events: wdb_topk_scan over the first 2^20 rows (threshold pre-pass) + "
+                                "wdb_topk_scan over the shard with the final selection and SELECT evaluation fused into its last CTA"),
            "merge_ms": max(per - ms_local / args.steps, 0.0),
            "collectives": ["ncclAllGather(80 B per rank: 5 x (key f32, value f32, global row i64))"] if world > 1 else [],
            "gpu_launches": launches, "clocks": clocks, "result_checked": ok}

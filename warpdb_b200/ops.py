@@ -263,6 +263,25 @@ class ZoneMap:
             pass
 
 
+def upload_column(host, name="col", device=0, zone_rows=0):
+    """Resident ingest of one host column (wdb_upload_column): a NumPy array or CPU tensor (pinned or pageable) goes to
+    the device in asynchronous chunks while its zone map is built chunk by chunk behind the copies.
+    Returns (device tensor, ZoneMap, (min, max))."""
+    t = host if isinstance(host, torch.Tensor) else torch.from_numpy(host)
+    if t.is_cuda or not t.is_contiguous() or t.dim() != 1 or t.dtype not in _TORCH2DT:
+        raise wc.WarpcoreError("upload_column needs a contiguous 1-D CPU tensor of int32/int64/float32/float64")
+    out = torch.empty(t.shape[0], dtype=t.dtype, device=f"cuda:{device}")
+    cols, _ = wc.make_cols([(name, _TORCH2DT[t.dtype], t.data_ptr(), t.shape[0])])
+    zm = ZoneMap.__new__(ZoneMap)
+    zm.device, zm.rows, zm.handle = device, t.shape[0], C.c_void_p()
+    lo, hi = C.c_double(0), C.c_double(0)
+    wc.check(wc.lib().wdb_upload_column(device, _stream(device), cols, out.data_ptr(), zone_rows, C.byref(zm.handle), C.byref(lo), C.byref(hi)))
+    zr, nz = C.c_int64(0), C.c_int64(0)
+    wc.check(wc.lib().wdb_zonemap_info(zm.handle, C.byref(zr), C.byref(nz)))
+    zm.zone_rows, zm.nzones = zr.value, nz.value
+    return out, zm, (lo.value, hi.value)
+
+
 def project_filter_pruned(table, expr, cond, preds, mode=wc.DENSE_ZERO, out=None, sync=True):
     """wdb_project_filter_pruned.  preds: list of (ZoneMap, op, constant) with op in > >= < <= == != and
     every term implied by `cond`.  Returns (out, count, zones_live)."""
