@@ -541,6 +541,9 @@ def run_ours(args):
     from warpdb_b200 import _core as wc, ops
     wc.check(wc.lib().wdb_init(local))
     wc.set_udf_source(UDF)
+    for k, v in os.environ.items():   # tuning experiments: WARPDB_OPT_group__dense_waves=1 -> option group.dense_waves
+        if k.startswith("WARPDB_OPT_"):
+            wc.set_option(k[len("WARPDB_OPT_"):].replace("__", "."), int(v))
     peak, peak_src = measured_peak()
     sampler = ClockSampler(local) if rank == 0 else None
     rows = args.rows or PROJECTION_ROWS_PER_GPU

@@ -384,7 +384,11 @@ int wdb_multi_group_agg(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int 
     bool overlap_failed = false;
     if (c->nranks > 1 && opt("multi.overlap_slices", 1)) {
       if (!c->side) {
-        WDB_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        WDB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        // highest priority: the exchange's CTAs take the first CTA slots the aggregation kernel frees (its CTAs are
+        // kept short while an exchange may be pending: group.dense_waves below)
+        WDB_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
         WDB_CUDA(cudaEventCreateWithFlags(&c->ev_slice, cudaEventDisableTiming));
         WDB_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
       }

@@ -648,7 +648,10 @@ int wdb_agg_consume(wdb_agg_t *t, void *stream, const wdb_col_t *cols, int ncols
   nb = std::max(1, std::min<int>(nb, (int)opt("group.ctas_per_sm", (t->dense_live && p.wp_ids == 0) ? 2 : 8)));
   const int64_t tile_rows = (int64_t)p.block * p.unroll * p.vec;
   const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
-  unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)d->num_sms * nb));
+  // several waves of short CTAs instead of one persistent wave while a cross-GPU exchange of the previous table slice may
+  // be waiting for CTA slots on a side stream (ops_comm.cu): a persistent grid would keep every SM until the kernel ends
+  const int64_t waves = t->after_slice ? std::max<int64_t>(1, opt("group.dense_waves", 8)) : 1;
+  unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)d->num_sms * nb * waves));
   std::vector<const void *> ptrs;
   for (const auto &u : p.spec.used) ptrs.push_back(cols[u.table_index].dptr);
   if (ptrs.empty()) ptrs.push_back(nullptr);
