@@ -350,11 +350,11 @@ int wdb_multi_group_agg(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int 
   if (expected_groups <= 0) expected_groups = 1 << 16;
   char *sc;
   if (comm_scratch(c, 256 + 8 * (size_t)c->nranks, &sc)) return 1;
-  long long *d_stat = (long long *)sc;            // [lo, -hi, -rows] (MIN all-reduce) | groups | spare
+  long long *d_stat = (long long *)sc;            // [lo, -hi, -max rows, min rows] (MIN all-reduce) | groups | spare
   long long *d_total = d_stat + 4;
 
   // 1. the GLOBAL key range (every rank must take the same path and index the same table layout)
-  long long st[3] = {INT64_MAX, INT64_MAX, -(long long)n_local};
+  long long st[4] = {INT64_MAX, INT64_MAX, -(long long)n_local, (long long)n_local};   // MIN-reduced: lo, -hi, -max rows, min rows
   if (range_known) { st[0] = key_lo; st[1] = -key_hi; }
   else if (n_local > 0) {
     KeyRange r{false, 0, -1};
@@ -362,13 +362,13 @@ int wdb_multi_group_agg(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int 
     if (r.known) { st[0] = r.lo; st[1] = -r.hi; }
   }
   if (c->nranks > 1) {
-    WDB_CUDA(cudaMemcpyAsync(d_stat, st, 24, cudaMemcpyHostToDevice, s));
-    if (allreduce(c, d_stat, 3, ncclInt64, ncclMin, s)) return 1;
-    WDB_CUDA(cudaMemcpyAsync(st, d_stat, 24, cudaMemcpyDeviceToHost, s));
+    WDB_CUDA(cudaMemcpyAsync(d_stat, st, 32, cudaMemcpyHostToDevice, s));
+    if (allreduce(c, d_stat, 4, ncclInt64, ncclMin, s)) return 1;
+    WDB_CUDA(cudaMemcpyAsync(st, d_stat, 32, cudaMemcpyDeviceToHost, s));
     WDB_CUDA(cudaStreamSynchronize(s));
   }
   const bool known = st[0] != INT64_MAX && st[1] != INT64_MAX;
-  const int64_t lo = known ? st[0] : 0, hi = known ? -st[1] : -1, span = hi - lo + 1, rows_max = -st[2];
+  const int64_t lo = known ? st[0] : 0, hi = known ? -st[1] : -1, span = hi - lo + 1, rows_max = -st[2], rows_min = st[3];
   const bool fast = known && !(needs & WDB_NEED_FIRST_BIT) && span <= opt("group.dense_max_span", 1 << 26) &&
                     (span <= (1 << 20) || span <= 4 * rows_max * c->nranks);
 
@@ -382,7 +382,11 @@ int wdb_multi_group_agg(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int 
     // last slice's exchange is exposed (10 M keys, 8 GPUs: 0.34 ms of NCCL for 80 MB, half of it hidden).
     int64_t reduced_to = 0;   // entries [0, reduced_to) have been all-reduced slice by slice
     bool overlap_failed = false;
-    if (c->nranks > 1 && opt("multi.overlap_slices", 1)) {
+    // Every rank must issue the same collectives: the slice-by-slice exchange is armed only where EVERY rank is sure to
+    // take the sliced direct-addressed path (the decision of wdb_agg_consume, evaluated on the smallest shard)
+    const bool all_sliced = rows_min > 0 && span >= opt("group.dense_min_span", 32768) && (span <= (1 << 20) || span <= 4 * rows_min) &&
+                            span > opt("group.wp_max_span", 4096);
+    if (c->nranks > 1 && all_sliced && opt("multi.overlap_slices", 1)) {
       if (!c->side) {
         int prio_lo = 0, prio_hi = 0;
         WDB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
