@@ -489,9 +489,9 @@ int wdb_multi_group_agg(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int 
   }
   // gathered arrays: keys i32 | sums f64 | counts i64 | mins f64 | maxs f64 | first i64, each [nranks][gmax]
   const size_t G = (size_t)((gmax + 1) / 2 * 2), W = (size_t)c->nranks;
-  char *buf = nullptr;
-  WDB_CUDA(cudaMallocAsync((void **)&buf, W * G * (4 + 8 * 5) + 64, s));
-  char *p = buf;
+  Scratch gathered;
+  WDB_CUDA(gathered.alloc(W * G * (4 + 8 * 5) + 64, s));
+  char *p = gathered.as<char>();
   double *a_sums = (double *)p; p += W * G * 8;
   long long *a_cnts = (long long *)p; p += W * G * 8;
   double *a_mins = (double *)p; p += W * G * 8;
@@ -504,10 +504,8 @@ int wdb_multi_group_agg(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int 
       wdb_agg_export(t, stream, needs & WDB_NEED_SUM_BIT ? WDB_SUM : (needs & WDB_NEED_CNT_BIT ? WDB_COUNT : WDB_MIN), WDB_ORDER_KEY_ASC, a_keys + me, nullptr,
                      (needs & WDB_NEED_SUM_BIT) ? a_sums + me : nullptr, (needs & WDB_NEED_CNT_BIT) ? (int64_t *)a_cnts + me : nullptr,
                      (needs & WDB_NEED_MINMAX_BIT) ? a_mins + me : nullptr, (needs & WDB_NEED_MINMAX_BIT) ? a_maxs + me : nullptr,
-                     (needs & WDB_NEED_FIRST_BIT) ? (int64_t *)a_first + me : nullptr, (int64_t)G, &gchk)) {
-    cudaFreeAsync(buf, s);
+                     (needs & WDB_NEED_FIRST_BIT) ? (int64_t *)a_first + me : nullptr, (int64_t)G, &gchk))
     return 1;
-  }
   {
     WDB_NCCL(g_nccl.GroupStart());
     int rc = allgather_inplace(c, (char *)a_keys, G * 4, s);
@@ -516,26 +514,23 @@ int wdb_multi_group_agg(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int 
     if (needs & WDB_NEED_MINMAX_BIT) { rc |= allgather_inplace(c, (char *)a_mins, G * 8, s); rc |= allgather_inplace(c, (char *)a_maxs, G * 8, s); }
     if (needs & WDB_NEED_FIRST_BIT) rc |= allgather_inplace(c, (char *)a_first, G * 8, s);
     WDB_NCCL(g_nccl.GroupEnd());
-    if (rc) { cudaFreeAsync(buf, s); return 1; }
+    if (rc) return 1;
   }
   wdb_agg *m = nullptr;
   {  // capacity: the distinct keys of all partials, rounded up to a power of two so that repeated queries reuse the table
     int64_t want = 1024;
     while (want < gsum) want <<= 1;
-    if (comm_table(c, kRoleMerge, needs, want, s, &m)) { cudaFreeAsync(buf, s); return 1; }
+    if (comm_table(c, kRoleMerge, needs, want, s, &m)) return 1;
   }
-  if (wdb_agg_set_key_range(m, known ? 1 : 0, lo, hi)) { cudaFreeAsync(buf, s); return 1; }
+  if (wdb_agg_set_key_range(m, known ? 1 : 0, lo, hi)) return 1;
   for (int r = 0; r < c->nranks; ++r) {
     const size_t o = (size_t)r * G;
-    if (counts[r] > 0 && wdb_agg_merge(m, stream, a_keys + o, a_sums + o, (const int64_t *)a_cnts + o, a_mins + o, a_maxs + o, (const int64_t *)a_first + o, counts[r])) {
-      cudaFreeAsync(buf, s);
+    if (counts[r] > 0 && wdb_agg_merge(m, stream, a_keys + o, a_sums + o, (const int64_t *)a_cnts + o, a_mins + o, a_maxs + o, (const int64_t *)a_first + o, counts[r]))
       return 1;
-    }
   }
   int64_t g = 0;
-  const int rc = wdb_agg_export(m, stream, agg, order, d_keys, d_vals, nullptr, nullptr, nullptr, nullptr, nullptr, cap, &g);
-  cudaFreeAsync(buf, s);
-  if (rc) return 1;
+  if (wdb_agg_export(m, stream, agg, order, d_keys, d_vals, nullptr, nullptr, nullptr, nullptr, nullptr, cap, &g)) return 1;
+  gathered.release();
   long long gg = g;
   if (d_groups) WDB_CUDA(cudaMemcpyAsync(d_groups, &gg, 8, cudaMemcpyHostToDevice, s));
   if (h_groups) *h_groups = g;
@@ -584,17 +579,16 @@ int wdb_multi_topk(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int ncols
   }
   // large limits: K best (value, key) pairs per rank, gathered in rank order (= global row order among
   // equal keys), one stable sort of the candidates, slice
-  float *buf = nullptr;
   const size_t W = (size_t)c->nranks;
-  WDB_CUDA(cudaMallocAsync((void **)&buf, (W * (size_t)K * 4 + 2 * W * (size_t)K) * sizeof(float) + 64, s));
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc((W * (size_t)K * 4 + 2 * W * (size_t)K) * sizeof(float) + 64, s));
+  float *buf = scratch.as<float>();
   float *g_vals = buf, *g_keys = buf + W * K, *s_vals = g_keys + W * K, *s_keys = s_vals + W * K;
   int64_t c_local = 0;
-  if (wdb_topk(d->id, stream, cols, ncols, key_expr, val_expr, cond, descending, K, 0, n_local, g_vals + (size_t)c->rank * K, g_keys + (size_t)c->rank * K, &c_local)) {
-    cudaFreeAsync(buf, s);
+  if (wdb_topk(d->id, stream, cols, ncols, key_expr, val_expr, cond, descending, K, 0, n_local, g_vals + (size_t)c->rank * K, g_keys + (size_t)c->rank * K, &c_local))
     return 1;
-  }
   char *sc;
-  if (comm_scratch(c, 8 * W + 64, &sc)) { cudaFreeAsync(buf, s); return 1; }
+  if (comm_scratch(c, 8 * W + 64, &sc)) return 1;
   long long *d_counts = (long long *)sc, cl = c_local;
   WDB_CUDA(cudaMemcpyAsync(d_counts + c->rank, &cl, 8, cudaMemcpyHostToDevice, s));
   std::vector<long long> counts(W, cl);
@@ -604,7 +598,7 @@ int wdb_multi_topk(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int ncols
     rc |= allgather_inplace(c, (char *)g_vals, (size_t)K * 4, s);
     rc |= allgather_inplace(c, (char *)g_keys, (size_t)K * 4, s);
     WDB_NCCL(g_nccl.GroupEnd());
-    if (rc) { cudaFreeAsync(buf, s); return 1; }
+    if (rc) return 1;
     WDB_CUDA(cudaMemcpyAsync(counts.data(), d_counts, 8 * W, cudaMemcpyDeviceToHost, s));
     WDB_CUDA(cudaStreamSynchronize(s));
   }
@@ -616,14 +610,14 @@ int wdb_multi_topk(wdb_comm_t *c, void *stream, const wdb_col_t *cols, int ncols
     }
     total += counts[r];
   }
-  if (total > 0 && sort_f32(d, s, s_keys, s_vals, total, descending == 0)) { cudaFreeAsync(buf, s); return 1; }
+  if (total > 0 && sort_f32(d, s, s_keys, s_vals, total, descending == 0)) return 1;
   const long long m = std::max<int64_t>(0, std::min<int64_t>(k, total - offset));
   if (m > 0) {
     if (d_out_vals) WDB_CUDA(cudaMemcpyAsync(d_out_vals, s_vals + offset, (size_t)m * 4, cudaMemcpyDeviceToDevice, s));
     if (d_out_keys) WDB_CUDA(cudaMemcpyAsync(d_out_keys, s_keys + offset, (size_t)m * 4, cudaMemcpyDeviceToDevice, s));
   }
   if (d_n) WDB_CUDA(cudaMemcpyAsync(d_n, &m, 8, cudaMemcpyHostToDevice, s));
-  WDB_CUDA(cudaFreeAsync(buf, s));
+  scratch.release();
   WDB_CUDA(cudaStreamSynchronize(s));
   if (h_n) *h_n = m;
   return 0;

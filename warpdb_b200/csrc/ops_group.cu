@@ -414,8 +414,9 @@ int auto_key_range(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncols, 
   const int block = kKeyRangeBlock, unroll = kKeyRangeUnroll, vec = kKeyRangeVec;
   Kernel k;
   if (get_kernel(d, gen_source(spec), "wdb_keyrange.cu", "wdb_keyrange", &k)) return 1;
-  int *d_out = nullptr;
-  WDB_CUDA(cudaMallocAsync((void **)&d_out, 8, s));
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc(8, s));
+  int *d_out = scratch.as<int>();
   const int init[2] = {INT32_MAX, INT32_MIN};
   WDB_CUDA(cudaMemcpyAsync(d_out, init, 8, cudaMemcpyHostToDevice, s));
   const int64_t tile_rows = (int64_t)block * unroll * vec;
@@ -427,18 +428,18 @@ int auto_key_range(Device *d, cudaStream_t s, const wdb_col_t *cols, int ncols, 
   if (launch(k, grid, block, 0, s, args)) return 1;
   int h[2];
   WDB_CUDA(cudaMemcpyAsync(h, d_out, 8, cudaMemcpyDeviceToHost, s));
-  WDB_CUDA(cudaFreeAsync(d_out, s));
   WDB_CUDA(cudaStreamSynchronize(s));
   if (h[0] <= h[1]) *out = KeyRange{true, h[0], h[1]};
   return 0;
 }
 
 // ---- direct-addressed side table: host side -------------------------------------------------------
-struct DenseScratch { char *buf = nullptr; unsigned *tile_counts; unsigned long long *tile_offsets, *total; long long ntiles; };
+struct DenseScratch { Scratch mem; char *buf = nullptr; unsigned *tile_counts; unsigned long long *tile_offsets, *total; long long ntiles; };
 static int dense_scratch(wdb_agg *t, cudaStream_t s, DenseScratch *sc) {
   sc->ntiles = ((long long)t->T.dspan + kDenseTile - 1) / kDenseTile;
   const size_t a = ((size_t)sc->ntiles * 4 + 15) & ~(size_t)15;
-  WDB_CUDA(cudaMallocAsync((void **)&sc->buf, a + (size_t)sc->ntiles * 8 + 16, s));
+  WDB_CUDA(sc->mem.alloc(a + (size_t)sc->ntiles * 8 + 16, s));
+  sc->buf = sc->mem.as<char>();
   sc->tile_counts = (unsigned *)sc->buf;
   sc->tile_offsets = (unsigned long long *)(sc->buf + a);
   sc->total = sc->tile_offsets + sc->ntiles;
@@ -472,7 +473,6 @@ static int dense_flush(wdb_agg *t, cudaStream_t s) {
                                                                                                     nullptr, nullptr, nullptr, nullptr)));
   stats().launches++;
   WDB_CUDA(cudaGetLastError());
-  WDB_CUDA(cudaFreeAsync(sc.buf, s));
   t->dense_live = false;
   t->T.dspan = 0;
   return 0;
@@ -525,7 +525,6 @@ int agg_export_dense_async(wdb_agg *t, cudaStream_t s, int agg, int order, int32
                                                                                                     (long long)cap, d_keys, d_vals, d_sums, (long long *)d_counts, d_mins, d_maxs)));
   stats().launches++;
   WDB_CUDA(cudaGetLastError());
-  WDB_CUDA(cudaFreeAsync(sc.buf, s));
   return 0;
 }
 
@@ -746,8 +745,7 @@ int wdb_agg_size(wdb_agg_t *t, void *stream, int64_t *h_groups) {
     if (wdb::dense_rank(t, s, &sc)) return 1;
     unsigned long long total = 0;
     WDB_CUDA(cudaMemcpyAsync(&total, sc.total, 8, cudaMemcpyDeviceToHost, s));
-    WDB_CUDA(cudaFreeAsync(sc.buf, s));
-    WDB_CUDA(cudaStreamSynchronize(s));
+      WDB_CUDA(cudaStreamSynchronize(s));
     *h_groups += (int64_t)total;
   }
   return 0;
@@ -785,15 +783,14 @@ int wdb_agg_export(wdb_agg_t *t, void *stream, int agg, int order, int32_t *d_ke
       WDB_CUDA(cudaMemcpyAsync(&total, sc.total, 8, cudaMemcpyDeviceToHost, s));
       WDB_CUDA(cudaStreamSynchronize(s));
       if (h_groups) *h_groups = (int64_t)total;
-      if ((long long)total > cap) { cudaFreeAsync(sc.buf, s); return fail("%lld groups exceed the output capacity %lld", (long long)total, (long long)cap); }
+      if ((long long)total > cap) return fail("%lld groups exceed the output capacity %lld", (long long)total, (long long)cap);
       if (total) {
         WDB_DENSE_DISPATCH(t->needs, (dense_emit_kernel<N><<<(unsigned)sc.ntiles, kDenseBlock, 0, s>>>(t->T, sc.tile_offsets, sc.total, order == WDB_ORDER_KEY_DESC, agg, 0,
                                                                                                       (long long)cap, d_keys, d_vals, d_sums, (long long *)d_counts, d_mins, d_maxs)));
         stats().launches++;
         WDB_CUDA(cudaGetLastError());
       }
-      WDB_CUDA(cudaFreeAsync(sc.buf, s));
-      WDB_CUDA(cudaStreamSynchronize(s));
+          WDB_CUDA(cudaStreamSynchronize(s));
       return 0;
     }
     if (wdb::dense_flush(t, s) || read_meta(t, s, meta)) return 1;
@@ -803,9 +800,10 @@ int wdb_agg_export(wdb_agg_t *t, void *stream, int agg, int order, int32_t *d_ke
   if (g == 0) return 0;
   if (g > cap) return fail("%lld groups exceed the output capacity %lld", g, (long long)cap);
   const long long slots = t->cap + 1;
-  char *buf = nullptr;
   const size_t kb = 8 * (size_t)g, pb = 4 * (size_t)g;
-  WDB_CUDA(cudaMallocAsync((void **)&buf, 2 * kb + 2 * pb + 64, s));
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc(2 * kb + 2 * pb + 64, s));
+  char *buf = scratch.as<char>();
   unsigned long long *sk = (unsigned long long *)buf, *skt = (unsigned long long *)(buf + kb);
   unsigned *sp = (unsigned *)(buf + 2 * kb), *spt = (unsigned *)(buf + 2 * kb + pb);
   unsigned long long *counter = (unsigned long long *)(buf + 2 * kb + 2 * pb);
@@ -818,7 +816,6 @@ int wdb_agg_export(wdb_agg_t *t, void *stream, int agg, int order, int32_t *d_ke
                                                   (long long *)d_first);
   stats().launches += 2;
   WDB_CUDA(cudaGetLastError());
-  WDB_CUDA(cudaFreeAsync(buf, s));
   WDB_CUDA(cudaStreamSynchronize(s));
   return 0;
 }

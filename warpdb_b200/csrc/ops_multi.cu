@@ -202,21 +202,21 @@ int wdb_column_minmax(int device, void *stream, const wdb_col_t *col, double *h_
   if (col->len <= 0) { *h_min = 0; *h_max = 0; return 0; }
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = (unsigned)std::min<int64_t>((col->len + 255) / 256, (int64_t)d->num_sms * 8);
-  double *part = nullptr;
-  WDB_CUDA(cudaMallocAsync((void **)&part, sizeof(double) * 2 * grid, s));
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc(sizeof(double) * 2 * grid, s));
+  double *part = scratch.as<double>();
   switch (col->dtype) {
   case WDB_INT32: minmax_kernel<int><<<grid, 256, 0, s>>>((const int *)col->dptr, col->len, part); break;
   case WDB_INT64: minmax_kernel<long long><<<grid, 256, 0, s>>>((const long long *)col->dptr, col->len, part); break;
   case WDB_FLOAT32: minmax_kernel<float><<<grid, 256, 0, s>>>((const float *)col->dptr, col->len, part); break;
   case WDB_FLOAT64: minmax_kernel<double><<<grid, 256, 0, s>>>((const double *)col->dptr, col->len, part); break;
-  default: cudaFreeAsync(part, s); return fail("column %s has a non-numeric type", col->name ? col->name : "?");
+  default: return fail("column %s has a non-numeric type", col->name ? col->name : "?");
   }
   stats().launches++;
   WDB_CUDA(cudaGetLastError());
   std::vector<double> h(2 * grid);
   WDB_CUDA(cudaMemcpyAsync(h.data(), part, sizeof(double) * 2 * grid, cudaMemcpyDeviceToHost, s));
   WDB_CUDA(cudaStreamSynchronize(s));
-  WDB_CUDA(cudaFreeAsync(part, s));
   double lo = h[0], hi = h[1];
   for (unsigned i = 1; i < grid; ++i) { lo = std::min(lo, h[2 * i]); hi = std::max(hi, h[2 * i + 1]); }
   *h_min = lo;

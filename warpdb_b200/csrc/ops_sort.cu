@@ -266,7 +266,9 @@ int radix_sort(Device *d, cudaStream_t s, K *keys, K *tmp_keys, unsigned *pay, u
   const long long nchunks = (n + chunk - 1) / chunk;
   const size_t hist_bytes = sizeof(unsigned) * 256 * (size_t)nchunks, offs_bytes = sizeof(long long) * 256 * (size_t)nchunks;
   void *hist = nullptr;
-  WDB_CUDA(cudaMallocAsync(&hist, hist_bytes + offs_bytes, s));
+  Scratch hist_scratch;
+  WDB_CUDA(hist_scratch.alloc(hist_bytes + offs_bytes, s));
+  hist = hist_scratch.p;
   unsigned *d_hist = (unsigned *)hist;
   long long *d_offs = (long long *)((char *)hist + hist_bytes);
   K *src = keys, *dst = tmp_keys;
@@ -287,7 +289,6 @@ int radix_sort(Device *d, cudaStream_t s, K *keys, K *tmp_keys, unsigned *pay, u
     WDB_CUDA(cudaMemcpyAsync(keys, src, sizeof(K) * (size_t)n, cudaMemcpyDeviceToDevice, s));
     if (pay) WDB_CUDA(cudaMemcpyAsync(pay, psrc, sizeof(unsigned) * (size_t)n, cudaMemcpyDeviceToDevice, s));
   }
-  WDB_CUDA(cudaFreeAsync(hist, s));
   return 0;
 }
 template int radix_sort<unsigned>(Device *, cudaStream_t, unsigned *, unsigned *, unsigned *, unsigned *, long long, int);
@@ -299,8 +300,9 @@ int sort_f32(Device *d, cudaStream_t s, float *d_keys, float *d_payload, long lo
   if (small_sort(s, d_keys, reinterpret_cast<unsigned *>(d_payload), n, true, ascending)) { WDB_CUDA(cudaGetLastError()); return 0; }
   if (d_payload && n >= (1ll << 32)) return fail("ORDER BY with a separate SELECT expression is limited to 2^32 surviving rows (%lld given)", n);
   const size_t nb = sizeof(unsigned) * (size_t)n;
-  char *buf = nullptr;
-  WDB_CUDA(cudaMallocAsync((void **)&buf, nb * (d_payload ? 5 : 2), s));
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc(nb * (d_payload ? 5 : 2), s));
+  char *buf = scratch.as<char>();
   unsigned *k = (unsigned *)buf, *kt = (unsigned *)(buf + nb);
   unsigned *p = d_payload ? (unsigned *)(buf + 2 * nb) : nullptr, *pt = d_payload ? (unsigned *)(buf + 3 * nb) : nullptr;
   float *pv = d_payload ? (float *)(buf + 4 * nb) : nullptr;
@@ -315,7 +317,6 @@ int sort_f32(Device *d, cudaStream_t s, float *d_keys, float *d_payload, long lo
   }
   stats().launches += d_payload ? 4 : 2;
   WDB_CUDA(cudaGetLastError());
-  WDB_CUDA(cudaFreeAsync(buf, s));
   return 0;
 }
 
@@ -343,8 +344,9 @@ int wdb_sort_pairs(int device, void *stream, int32_t *d_keys, float *d_vals, int
   const long long n = count;
   if (small_sort(s, d_keys, reinterpret_cast<unsigned *>(d_vals), n, false, ascending != 0)) { WDB_CUDA(cudaGetLastError()); return 0; }
   const size_t nb = 4 * (size_t)n;
-  char *buf = nullptr;
-  WDB_CUDA(cudaMallocAsync((void **)&buf, nb * 3, s));
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc(nb * 3, s));
+  char *buf = scratch.as<char>();
   unsigned *k = (unsigned *)buf, *kt = (unsigned *)(buf + nb), *pt = (unsigned *)(buf + 2 * nb);
   const unsigned g = grid_for(d, n);
   i32_encode_kernel<<<g, 256, 0, s>>>(d_keys, k, n, ascending ? 0 : 1);
@@ -353,7 +355,6 @@ int wdb_sort_pairs(int device, void *stream, int32_t *d_keys, float *d_vals, int
   i32_decode_kernel<<<g, 256, 0, s>>>(k, d_keys, n, ascending ? 0 : 1);
   stats().launches += 2;
   WDB_CUDA(cudaGetLastError());
-  WDB_CUDA(cudaFreeAsync(buf, s));
   return 0;
 }
 }

@@ -151,15 +151,15 @@ int zone_live_ranges(Device *d, cudaStream_t s, const wdb_prune_t *preds, int np
   *live = 0;
   ranges->clear();
   if (nz == 0) return 0;
-  char *buf = nullptr;
-  WDB_CUDA(cudaMallocAsync((void **)&buf, (size_t)nz + 16, s));
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc((size_t)nz + 16, s));
+  char *buf = scratch.as<char>();
   WDB_CUDA(cudaMemsetAsync(buf, 0, 8, s));
   zone_mask_kernel<<<(unsigned)std::min<int64_t>((nz + 255) / 256, 4096), 256, 0, s>>>(P, nz, (unsigned char *)(buf + 16), (unsigned long long *)buf);
   stats().launches++;
   WDB_CUDA(cudaGetLastError());
   std::vector<unsigned char> h((size_t)nz);
   WDB_CUDA(cudaMemcpyAsync(h.data(), buf + 16, (size_t)nz, cudaMemcpyDeviceToHost, s));
-  WDB_CUDA(cudaFreeAsync(buf, s));
   WDB_CUDA(cudaStreamSynchronize(s));
   const int64_t zr = 1ll << z0->zshift;
   for (int64_t z = 0; z < nz;) {
@@ -335,8 +335,9 @@ int wdb_project_filter_pruned(int device, void *stream, const wdb_col_t *cols, i
     P.p[i] = DevPred{z->mins, z->maxs, preds[i].op, preds[i].value};
   }
   const int64_t nz = z0->nzones;
-  char *buf = nullptr;
-  WDB_CUDA(cudaMallocAsync((void **)&buf, (size_t)std::max<int64_t>(nz, 1) + 16, s));
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc((size_t)std::max<int64_t>(nz, 1) + 16, s));
+  char *buf = scratch.as<char>();
   unsigned long long *d_live = (unsigned long long *)buf;
   unsigned char *mask = (unsigned char *)(buf + 16);
   WDB_CUDA(cudaMemsetAsync(d_live, 0, 8, s));
@@ -363,7 +364,6 @@ int wdb_project_filter_pruned(int device, void *stream, const wdb_col_t *cols, i
     *h_zones_live = (int64_t)live;
   } else if (!rc && (h_count || d_count))
     WDB_CUDA(cudaStreamSynchronize(s));
-  WDB_CUDA(cudaFreeAsync(buf, s));
   return rc;
 }
 
@@ -410,8 +410,9 @@ int wdb_topk_pruned(int device, void *stream, const wdb_col_t *cols, int ncols, 
   // every run of live zones yields its K best (key, global row) pairs; the one-warp selection of the sharded
   // ORDER BY merges them (runs are ascending row ranges, so ties keep row order)
   const size_t per = (size_t)K * 16;
-  char *buf = nullptr;
-  WDB_CUDA(cudaMallocAsync((void **)&buf, per * ranges.size() + 64, s));
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc(per * ranges.size() + 64, s));
+  char *buf = scratch.as<char>();
   long long *d_cnt = (long long *)(buf + per * ranges.size());
   const std::string okey = order_key(key_expr, descending != 0);
   int rc = 0;
@@ -426,7 +427,6 @@ int wdb_topk_pruned(int device, void *stream, const wdb_col_t *cols, int ncols, 
     if (cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) rc = fail("CUDA error: top-k count read-back");
     *h_n = cnt;
   }
-  cudaFreeAsync(buf, s);
   return rc;
 }
 }
