@@ -180,6 +180,28 @@ int wdb_topk_pruned(int device, void *stream, const wdb_col_t *cols, int ncols, 
                     int descending, int64_t k, int64_t offset, int64_t n, float *d_out_vals, float *d_out_keys, int64_t *h_n,
                     const wdb_prune_t *preds, int npreds, int64_t *h_zones_live);
 
+/* ---- inner equi-join on integer keys.  `JOIN <table> ON <expr>` is parsed by the reference
+ * (JoinClause, include/expression.hpp:123-135; src/expression.cpp:375-401) and validated
+ * (src/warpdb.cpp:321-323) but never executed ("Currently JOIN loads the same table for
+ * demonstration purposes", include/warpdb.hpp:22); these entry points are what a query_sql that
+ * does execute it binds.  Result = every (probe row i, build row j) with probe_key[i] ==
+ * build_key[j], ordered by i, then j (nested-loop order).  Keys are WDB_INT32 or WDB_INT64 columns
+ * (the two sides may differ); the build side holds at most 2^32 - 1 rows.
+ *   wdb_join_build   sorts (key, row) of the build column once; the index can be probed many times
+ *   wdb_join_probe   d_probe_rows == d_build_rows == NULL: count only (*h_pairs); otherwise the pairs
+ *                    are written (cap = capacity of each array in pairs; more pairs than cap is an
+ *                    error and nothing is written).  Synchronous: returns after the stream drained.
+ *   wdb_gather       d_dst[i] = src[d_rows[i]] for i < count (4- and 8-byte column types; d_rows ==
+ *                    NULL copies the first count rows): materialises the columns a joined query reads,
+ *                    which the other operators then consume unchanged.  Rows are not range-checked. */
+typedef struct wdb_join wdb_join_t;
+int wdb_join_build(int device, void *stream, const wdb_col_t *build_key, wdb_join_t **out);
+int wdb_join_probe(wdb_join_t *j, void *stream, const wdb_col_t *probe_key, int64_t *d_probe_rows, int64_t *d_build_rows, int64_t cap,
+                   int64_t *h_pairs);
+int wdb_join_info(const wdb_join_t *j, int64_t *build_rows, int *key_dtype);
+int wdb_join_destroy(wdb_join_t *j);
+int wdb_gather(int device, void *stream, const wdb_col_t *src, const int64_t *d_rows, int64_t count, void *d_dst);
+
 /* ---- multi-GPU: run_multi_gpu_jit_host (include/multi_gpu_utils.hpp:10-12,
  * src/multi_gpu_utils.cpp:5-63).  Host columns in, host floats out; rows are split into
  * contiguous shards chunk = ceil(n/ndev) and all devices run concurrently on their own

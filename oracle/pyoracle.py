@@ -225,6 +225,21 @@ def sort_pairs(keys, vals, ascending=True):
     return k, v
 
 
+def join_pairs(probe, build, indexed=True):
+    """every (i, j) with probe[i] == build[j], ordered by i then j -> (probe_rows, build_rows) int64"""
+    p = np.ascontiguousarray(probe, dtype=np.int64)
+    b = np.ascontiguousarray(build, dtype=np.int64)
+    L = lib()
+    L.orc_join_pairs.restype = C.c_int64
+    L.orc_join_pairs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+    total = L.orc_join_pairs(p.ctypes.data, p.shape[0], b.ctypes.data, b.shape[0], int(indexed), None, None, 0)
+    pr = np.empty(total, dtype=np.int64)
+    br = np.empty(total, dtype=np.int64)
+    got = L.orc_join_pairs(p.ctypes.data, p.shape[0], b.ctypes.data, b.shape[0], int(indexed), pr.ctypes.data, br.ctypes.data, total)
+    assert got == total
+    return pr, br
+
+
 def shard_range(n, ndev, dev):
     s, e = C.c_int64(0), C.c_int64(0)
     lib().orc_shard_range(n, ndev, dev, C.byref(s), C.byref(e))

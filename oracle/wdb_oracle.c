@@ -1091,6 +1091,48 @@ int orc_topk(const orc_node *expr, const orc_node *cond, const orc_col_t *cols, 
   return 0;
 }
 
+/* ---- inner equi-join (definition: nested loop, probe-major) ------------------------------- */
+typedef struct { int64_t k, r; } kr_t;
+static void kr_msort(kr_t *a, kr_t *tmp, int64_t n) {   /* stable: equal keys keep their row order */
+  if (n < 2) return;
+  int64_t h = n / 2;
+  kr_msort(a, tmp, h);
+  kr_msort(a + h, tmp, n - h);
+  int64_t i = 0, j = h, o = 0;
+  while (i < h && j < n) tmp[o++] = (a[j].k < a[i].k) ? a[j++] : a[i++];
+  while (i < h) tmp[o++] = a[i++];
+  while (j < n) tmp[o++] = a[j++];
+  memcpy(a, tmp, sizeof(kr_t) * n);
+}
+int64_t orc_join_pairs(const int64_t *probe, int64_t n, const int64_t *build, int64_t m, int indexed,
+                       int64_t *out_probe, int64_t *out_build, int64_t cap) {
+  int64_t o = 0;
+  if (!indexed) {
+    for (int64_t i = 0; i < n; i++)
+      for (int64_t j = 0; j < m; j++)
+        if (probe[i] == build[j]) {
+          if (out_probe && o < cap) out_probe[o] = i;
+          if (out_build && o < cap) out_build[o] = j;
+          o++;
+        }
+    return o;
+  }
+  kr_t *a = (kr_t *)malloc(sizeof(kr_t) * (m ? m : 1)), *t = (kr_t *)malloc(sizeof(kr_t) * (m ? m : 1));
+  for (int64_t j = 0; j < m; j++) { a[j].k = build[j]; a[j].r = j; }
+  kr_msort(a, t, m);
+  for (int64_t i = 0; i < n; i++) {
+    int64_t lo = 0, hi = m;
+    while (lo < hi) { int64_t mid = lo + (hi - lo) / 2; if (a[mid].k < probe[i]) lo = mid + 1; else hi = mid; }
+    for (int64_t q = lo; q < m && a[q].k == probe[i]; q++) {
+      if (out_probe && o < cap) out_probe[o] = i;
+      if (out_build && o < cap) out_build[o] = a[q].r;
+      o++;
+    }
+  }
+  free(a); free(t);
+  return o;
+}
+
 void orc_shard_range(int64_t n, int ndev, int dev, int64_t *start, int64_t *end) { /* multi_gpu_utils.cpp:24-31 */
   int64_t chunk = (n + ndev - 1) / ndev;
   int64_t s = (int64_t)dev * chunk, e = s + chunk < n ? s + chunk : n;

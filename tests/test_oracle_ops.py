@@ -152,3 +152,20 @@ def test_stable_sorts_match_bubble_sort():
     f = rng.standard_normal(50).astype(np.float32)
     assert np.array_equal(orc.sort_float(f, True), np.sort(f))
     assert np.array_equal(orc.sort_float(f, False), np.sort(f)[::-1])
+
+
+def test_join_pairs_is_the_nested_loop():
+    # JOIN is parsed by the reference (src/expression.cpp:375-401) and never executed, so nothing of the
+    # reference pins it: the oracle states SQL's inner equi-join as the probe-major nested loop, and its
+    # indexed variant (what the larger GPU tests compare with) must enumerate the same pairs in the same order
+    rng = np.random.default_rng(5)
+    for n, m, span in [(0, 5, 3), (5, 0, 3), (1, 1, 1), (400, 300, 40), (300, 400, 100000), (64, 64, 1)]:
+        probe, build = rng.integers(-span, span, n), rng.integers(-span, span, m)
+        pi, pj = orc.join_pairs(probe, build, indexed=False)
+        qi, qj = orc.join_pairs(probe, build, indexed=True)
+        ii, jj = np.nonzero(probe[:, None] == build[None, :]) if n and m else (np.empty(0, np.int64), np.empty(0, np.int64))
+        assert np.array_equal(pi, ii) and np.array_equal(pj, jj)
+        assert np.array_equal(qi, ii) and np.array_equal(qj, jj)
+    lim = np.array([np.iinfo(np.int64).min, -1, 0, np.iinfo(np.int64).max])
+    i, j = orc.join_pairs(lim, lim[::-1].copy())
+    assert i.tolist() == [0, 1, 2, 3] and j.tolist() == [3, 2, 1, 0]

@@ -27,6 +27,7 @@ SYMBOLS = [
     "wdb_shard_range", "wdb_synth_f32", "wdb_synth_i32", "wdb_debug_compile", "wdb_free",
     "wdb_comm_unique_id", "wdb_comm_init_rank", "wdb_comm_init_all", "wdb_comm_destroy", "wdb_comm_info",
     "wdb_multi_project_filter", "wdb_multi_group_agg", "wdb_multi_topk", "wdb_multi_group_agg_host", "wdb_multi_topk_host",
+    "wdb_join_build", "wdb_join_probe", "wdb_join_info", "wdb_join_destroy", "wdb_gather",
 ]
 
 
@@ -109,6 +110,11 @@ def lib():
     L.wdb_multi_topk.argtypes = [vp, vp, PC, ci, cp, cp, cp, ci, i64, i64, i64, i64, vp, vp, vp, P64]
     L.wdb_multi_group_agg_host.argtypes = [ci, C.POINTER(ci), PC, ci, cp, cp, cp, ci, ci, i64, i64, vp, vp, i64, P64]
     L.wdb_multi_topk_host.argtypes = [ci, C.POINTER(ci), PC, ci, cp, cp, cp, ci, i64, i64, i64, vp, P64]
+    L.wdb_join_build.argtypes = [ci, vp, PC, C.POINTER(vp)]
+    L.wdb_join_probe.argtypes = [vp, vp, PC, vp, vp, i64, P64]
+    L.wdb_join_info.argtypes = [vp, P64, C.POINTER(ci)]
+    L.wdb_join_destroy.argtypes = [vp]
+    L.wdb_gather.argtypes = [ci, vp, PC, vp, i64, vp]
     _lib = L
     return L
 

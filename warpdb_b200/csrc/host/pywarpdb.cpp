@@ -97,6 +97,11 @@ PYBIND11_MODULE(pywarpdb, m) {
            },
            py::arg("expr"), py::arg("shared_memory") = false,
            "Return result as Arrow C Data Interface capsules (ArrowArray, ArrowSchema).")
+      .def("attach",
+           [](WarpDB &db, const std::string &name, const std::string &filepath, const std::vector<DataType> &schema) { db.attach(name, filepath, schema); },
+           py::arg("name"), py::arg("filepath"), py::arg("schema") = std::vector<DataType>{},
+           "Load another table and make it joinable by name: ... FROM t JOIN name ON t.k = name.k")
+      .def("last_join_rows", &WarpDB::last_join_rows)
       .def("num_rows", &WarpDB::num_rows)
       .def("set_zone_pruning", &WarpDB::set_zone_pruning)
       .def("last_zones_live", &WarpDB::last_zones_live)

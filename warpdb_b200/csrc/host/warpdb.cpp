@@ -328,6 +328,166 @@ std::vector<float> WarpDB::query_sql(const std::string &sql) {
   } catch (const std::exception &e) {
     throw std::runtime_error(std::string("Failed to parse SQL: ") + e.what());
   }
+  last_join_rows_ = -1;
+  return ast.joins.empty() ? run_sql(ast) : run_sql_join(ast);
+}
+
+void WarpDB::attach(const std::string &name, const std::string &filepath, const std::vector<DataType> &schema) {
+  if (name.empty()) throw std::runtime_error("attach: empty table name");
+  attached_[name] = std::make_unique<WarpDB>(filepath, schema);
+}
+void WarpDB::attach(const std::string &name, Table device_table) {
+  if (name.empty()) throw std::runtime_error("attach: empty table name");
+  attached_[name] = std::make_unique<WarpDB>(std::move(device_table));
+}
+
+namespace {
+// every VariableNode below `n`, in evaluation order
+void collect_variables(ASTNode *n, std::vector<VariableNode *> *out) {
+  if (!n) return;
+  if (auto v = dynamic_cast<VariableNode *>(n)) out->push_back(v);
+  else if (auto b = dynamic_cast<BinaryOpNode *>(n)) { collect_variables(b->left.get(), out); collect_variables(b->right.get(), out); }
+  else if (auto f = dynamic_cast<FunctionCallNode *>(n)) { for (auto &a : f->args) collect_variables(a.get(), out); }
+  else if (auto a = dynamic_cast<AggregationNode *>(n)) collect_variables(a->expr.get(), out);
+  else if (auto w = dynamic_cast<WindowFunctionNode *>(n)) {
+    collect_variables(w->expr.get(), out);
+    for (auto &p : w->partition_by) collect_variables(p.get(), out);
+    if (w->order_by) collect_variables(w->order_by->expr.get(), out);
+  }
+}
+const ColumnDesc *find_column(const Table &t, const std::string &name) {
+  for (const auto &c : t.columns)
+    if (c.name == name) return &c;
+  return nullptr;
+}
+bool is_int_key(DataType t) { return t == DataType::Int32 || t == DataType::Int64; }
+}  // namespace
+
+// FROM a JOIN b ON a.k = b.k [JOIN c ON ...]: the joins run first, left to right, on row numbers
+// only (late materialisation) -- every source table keeps one int64 row map into the joined row set;
+// a join probes the new table's sorted key index (wdb_join_build / wdb_join_probe) with the key of
+// the rows joined so far, and the row maps of the earlier sources are carried through the resulting
+// pairs.  The columns the rest of the statement reads are then gathered once (wdb_gather) and the
+// statement runs on them like on any other table (run_sql): WHERE, GROUP BY, ORDER BY ... all see
+// the joined rows in nested-loop order (rows of the left side in order, matches of one row in the
+// right table's row order).
+std::vector<float> WarpDB::run_sql_join(QueryAST &ast) {
+  struct Source { std::string name; const Table *table; std::shared_ptr<DeviceBuffer> rows; };   // rows == null: identity
+  std::vector<Source> sources{{ast.from_table, &table_, nullptr}};
+  int64_t joined_rows = table_.num_rows;
+
+  // name -> (source, column): "<table>.<column>" picks the source by name, a bare name the first source
+  // that has the column (`prefer_last`: the newest one first -- the right operand of an ON condition)
+  auto resolve = [&](const std::string &name, bool prefer_last, const char *ctx) -> std::pair<int, const ColumnDesc *> {
+    std::vector<std::pair<int, const ColumnDesc *>> matches;
+    const auto dot = name.find('.');
+    for (int i = 0; i < static_cast<int>(sources.size()); ++i) {
+      const ColumnDesc *c = nullptr;
+      if (dot != std::string::npos && sources[i].name == name.substr(0, dot)) c = find_column(*sources[i].table, name.substr(dot + 1));
+      if (!c) c = find_column(*sources[i].table, name);   // a bare name, or a column literally called "a.b"
+      if (c) matches.emplace_back(i, c);
+    }
+    if (matches.empty()) throw std::runtime_error(std::string(ctx) + ": Unknown column: " + name);
+    return prefer_last ? matches.back() : matches.front();
+  };
+  auto gather_rows = [&](const ColumnDesc &c, const Table &t, const DeviceBuffer *rows, int64_t count, void *dst) {
+    const wdb_col_t col{c.name.c_str(), static_cast<int>(c.type), c.device_ptr, t.num_rows};
+    if (wdb_gather(0, nullptr, &col, rows ? rows->as<int64_t>() : nullptr, count, dst)) raise_core();
+  };
+
+  for (const JoinClause &jc : ast.joins) {
+    const auto at = attached_.find(jc.table);
+    const Table *right = at == attached_.end() ? &table_ : &at->second->table_;
+    sources.push_back({jc.table, right, nullptr});
+    const int new_source = static_cast<int>(sources.size()) - 1;
+    const auto *eq = dynamic_cast<const BinaryOpNode *>(jc.condition.get());
+    const auto *lv = eq ? dynamic_cast<const VariableNode *>(eq->left.get()) : nullptr;
+    const auto *rv = eq ? dynamic_cast<const VariableNode *>(eq->right.get()) : nullptr;
+    if (!eq || (eq->op != "=" && eq->op != "==") || !lv || !rv)
+      throw std::runtime_error("JOIN condition: only `<column> = <column>` is supported");
+    auto l = resolve(lv->name, false, "JOIN condition"), r = resolve(rv->name, true, "JOIN condition");
+    if ((l.first == new_source) == (r.first == new_source)) {   // `ON new.k = old.k`, or bare names the other way round
+      l = resolve(lv->name, true, "JOIN condition");
+      r = resolve(rv->name, false, "JOIN condition");
+    }
+    if ((l.first == new_source) == (r.first == new_source))
+      throw std::runtime_error("JOIN condition: must compare a column of " + jc.table + " with a column of the tables before it");
+    const auto &probe = l.first == new_source ? r : l;
+    const auto &build = l.first == new_source ? l : r;
+    if (!is_int_key(probe.second->type) || !is_int_key(build.second->type))
+      throw std::runtime_error("JOIN condition: key columns must be Int32 or Int64 (" + probe.second->name + ", " + build.second->name + ")");
+
+    // key of the rows joined so far
+    const Source &ps = sources[probe.first];
+    const size_t ksz = probe.second->type == DataType::Int32 ? 4 : 8;
+    std::unique_ptr<DeviceBuffer> probe_key;
+    wdb_col_t pk{probe.second->name.c_str(), static_cast<int>(probe.second->type), probe.second->device_ptr, joined_rows};
+    if (ps.rows) {
+      probe_key = std::make_unique<DeviceBuffer>(ksz * static_cast<size_t>(joined_rows));
+      gather_rows(*probe.second, *ps.table, ps.rows.get(), joined_rows, probe_key->p);
+      pk.dptr = probe_key->p;
+    }
+    const wdb_col_t bk{build.second->name.c_str(), static_cast<int>(build.second->type), build.second->device_ptr, right->num_rows};
+    wdb_join_t *index = nullptr;
+    if (wdb_join_build(0, nullptr, &bk, &index)) raise_core();
+    std::unique_ptr<wdb_join_t, int (*)(wdb_join_t *)> guard(index, wdb_join_destroy);
+    int64_t pairs = 0;
+    if (wdb_join_probe(index, nullptr, &pk, nullptr, nullptr, 0, &pairs)) raise_core();
+    if (pairs > 0x7fffffffll) throw std::runtime_error("JOIN produces " + std::to_string(pairs) + " rows; a table holds at most 2^31 - 1");
+    auto left_rows = std::make_shared<DeviceBuffer>(8 * static_cast<size_t>(pairs));
+    auto right_rows = std::make_shared<DeviceBuffer>(8 * static_cast<size_t>(pairs));
+    if (pairs && wdb_join_probe(index, nullptr, &pk, left_rows->as<int64_t>(), right_rows->as<int64_t>(), pairs, &pairs)) raise_core();
+    // carry the earlier sources' row maps through the pairs
+    for (int i = 0; i < new_source; ++i) {
+      if (!sources[i].rows) { sources[i].rows = left_rows; continue; }
+      auto composed = std::make_shared<DeviceBuffer>(8 * static_cast<size_t>(pairs));
+      const wdb_col_t old{"rows", WDB_INT64, sources[i].rows->p, joined_rows};
+      if (wdb_gather(0, nullptr, &old, left_rows->as<int64_t>(), pairs, composed->p)) raise_core();
+      sources[i].rows = composed;
+    }
+    sources[new_source].rows = right_rows;
+    joined_rows = pairs;
+  }
+  last_join_rows_ = joined_rows;
+
+  // materialise what the rest of the statement reads; the AST is renamed onto the gathered columns
+  std::vector<std::pair<ASTNode *, const char *>> clauses;
+  for (auto &e : ast.select_list) clauses.emplace_back(e.get(), "SELECT clause");
+  if (ast.where) clauses.emplace_back(ast.where->get(), "WHERE clause");
+  if (ast.group_by)
+    for (auto &k : ast.group_by->keys) clauses.emplace_back(k.get(), "GROUP BY");
+  if (ast.having) clauses.emplace_back(ast.having->get(), "HAVING clause");
+  if (ast.order_by) clauses.emplace_back(ast.order_by->expr.get(), "ORDER BY");
+  Table joined;
+  joined.num_rows = static_cast<int>(joined_rows);
+  std::vector<std::unique_ptr<DeviceBuffer>> owned;
+  std::map<std::pair<int, const ColumnDesc *>, std::string> made;
+  for (auto &cl : clauses) {
+    std::vector<VariableNode *> vars;
+    collect_variables(cl.first, &vars);
+    for (VariableNode *v : vars) {
+      const auto rc = resolve(v->name, false, cl.second);
+      auto it = made.find(rc);
+      if (it == made.end()) {
+        const std::string name = "wdbj" + std::to_string(made.size()) + "_" + rc.second->name.substr(rc.second->name.find('.') == std::string::npos ? 0 : rc.second->name.find_last_of('.') + 1);
+        const size_t esz = (rc.second->type == DataType::Int32 || rc.second->type == DataType::Float32) ? 4 : 8;
+        if (rc.second->type == DataType::String) throw std::runtime_error(std::string(cl.second) + ": string column " + rc.second->name + " cannot be evaluated");
+        owned.push_back(std::make_unique<DeviceBuffer>(esz * static_cast<size_t>(joined_rows)));
+        gather_rows(*rc.second, *sources[rc.first].table, sources[rc.first].rows.get(), joined_rows, owned.back()->p);
+        joined.columns.push_back(ColumnDesc{name, rc.second->type, owned.back()->p, static_cast<int>(joined_rows)});
+        it = made.emplace(rc, name).first;
+      }
+      v->name = it->second;
+    }
+  }
+  ast.joins.clear();
+  if (cudaDeviceSynchronize() != cudaSuccess) throw std::runtime_error("CUDA error: join materialisation failed");
+  WarpDB view(joined);          // does not own the columns: `owned` does
+  view.set_zone_pruning(false); // one-shot columns: a zone map would cost a pass and be used once
+  return view.run_sql(ast);
+}
+
+std::vector<float> WarpDB::run_sql(QueryAST &ast) {
   std::unordered_set<std::string> cols;
   for (const auto &c : table_.columns) cols.insert(c.name);
   auto validate_ctx = [&](const ASTNode *node, const char *ctx) {

@@ -2,6 +2,7 @@
 // running on the B200-native core (include/warpcore.h).
 #pragma once
 #include <map>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -23,8 +24,17 @@ public:
 
   // "<expr> [WHERE <cond>]" -> one float per table row; rows failing cond yield 0.0f
   std::vector<float> query(const std::string &expr);
-  // SELECT [DISTINCT] <expr|AGG(expr)> FROM t [WHERE c] [GROUP BY k] [HAVING h] [ORDER BY e [ASC|DESC]] [LIMIT n] [OFFSET m]
+  // SELECT [DISTINCT] <expr|AGG(expr)> FROM t [JOIN u ON t.a = u.b]... [WHERE c] [GROUP BY k] [HAVING h]
+  //        [ORDER BY e [ASC|DESC]] [LIMIT n] [OFFSET m]
   std::vector<float> query_sql(const std::string &sql);
+  // Make another table joinable under `name` (`... FROM t JOIN name ON t.k = name.k`).  Not in the
+  // reference: its WarpDB holds one table, parses JOIN clauses (src/expression.cpp:375-401) and never
+  // executes them; a JOIN naming a table that was not attached joins this table with itself
+  // ("Currently JOIN loads the same table for demonstration purposes", include/warpdb.hpp:22).
+  void attach(const std::string &name, const std::string &filepath, const std::vector<DataType> &schema = {});
+  void attach(const std::string &name, Table device_table);
+  // rows the last JOIN query produced before WHERE (-1: the last query_sql had no JOIN)
+  long long last_join_rows() const { return last_join_rows_; }
   // same as query() over every visible GPU (row-range shards of the host copy of the table)
   std::vector<float> query_multi_gpu(const std::string &expr);
   // query_sql() over every visible GPU: GROUP BY aggregates and ORDER BY ... LIMIT run on row-range
@@ -61,6 +71,8 @@ private:
   std::vector<PruneTerm> prune_terms(const ASTNode *cond) const;
   void *zonemap_for(const std::string &column);   // wdb_zonemap_t*, nullptr if not prunable
   std::vector<struct wdb_prune> prune_preds(const ASTNode *cond_ast);
+  std::vector<float> run_sql(QueryAST &ast);        // everything after parsing, on table_
+  std::vector<float> run_sql_join(QueryAST &ast);   // inner equi-joins first, then run_sql on the joined columns
   int filter_project(const std::string &expr, const std::string &cond, const ASTNode *cond_ast, float *d_out, int mode,
                      long long *count);
 
@@ -71,4 +83,6 @@ private:
   std::map<std::string, void *> zonemaps_;
   std::map<std::string, std::pair<long long, long long>> key_ranges_;   // min/max of integer GROUP BY columns
   long long last_zones_live_ = -1, last_zones_total_ = -1;
+  std::map<std::string, std::unique_ptr<WarpDB>> attached_;
+  long long last_join_rows_ = -1;
 };

@@ -1,0 +1,319 @@
+// ops_join.cu -- inner equi-join on integer keys (the last one).
+//
+// Reference: `JOIN <table> ON <expr>` is parsed into QueryAST::joins (src/expression.cpp:375-401,
+// include/expression.hpp:123-135) and its condition is validated (src/warpdb.cpp:321-323); nothing
+// in the reference executes it ("Currently JOIN loads the same table for demonstration purposes",
+// include/warpdb.hpp:22).  The semantics here are SQL's: every pair (i, j) with
+// probe_key[i] == build_key[j], in nested-loop order -- ascending i, and ascending j within one i --
+// which is what the oracle's orc_join_pairs enumerates.
+//
+// Sort-based, so the result order needs no post-pass and equal keys on either side are handled:
+//   build   (key, row) pairs of the build column, stable LSD radix sort by key (ops_sort.cu); equal
+//           keys keep their row order
+//   probe   two streaming passes over the probe column.  Pass 1 counts the matches of every 1 024-row
+//           tile (lower / upper bound in the sorted keys, which stay in L2 for dimension-sized build
+//           sides), one block scan turns the tile counts into offsets, pass 2 repeats the searches
+//           and writes the pairs at tile offset + in-tile prefix.  Nothing per probe row is kept
+//           between the passes: HBM traffic is 2 x the probe keys + 16 B per emitted pair.
+//   gather  dst[i] = src[rows[i]]: late materialisation of the columns a query reads, after which
+//           every other operator of the core (filter / project / GROUP BY / top-k) runs unchanged
+//           on the joined columns.
+#include <algorithm>
+
+#include "core.hpp"
+
+namespace wdb {
+
+template <class K>
+int radix_sort(Device *d, cudaStream_t s, K *keys, K *tmp_keys, unsigned *pay, unsigned *tmp_pay, long long n, int key_bits);
+
+constexpr int kJoinBlock = 256;
+constexpr int kJoinWarps = kJoinBlock / 32;
+constexpr int kJoinRounds = 4;
+constexpr int kJoinTile = kJoinBlock * kJoinRounds;
+
+// order-preserving signed -> unsigned, and the payload (= build row) alongside
+template <class S, class U>
+__global__ void join_encode_kernel(const S *__restrict__ in, U *__restrict__ out, unsigned *__restrict__ rows, long long n) {
+  constexpr U kSign = (U)1 << (8 * sizeof(U) - 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    out[i] = (U)in[i] ^ kSign;
+    rows[i] = (unsigned)i;
+  }
+}
+template <class S, class U>
+__global__ void join_decode_kernel(U *keys, long long n) {   // in place: same width
+  constexpr U kSign = (U)1 << (8 * sizeof(U) - 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const S v = (S)(keys[i] ^ kSign);
+    reinterpret_cast<S *>(keys)[i] = v;
+  }
+}
+
+// [lb, ub) = positions of `v` in the ascending keys[0..m)
+template <class B>
+__device__ __forceinline__ void equal_range(const B *__restrict__ keys, unsigned m, long long v, unsigned *lb, unsigned *ub) {
+  unsigned lo = 0, hi = m;
+  while (lo < hi) {
+    const unsigned mid = lo + ((hi - lo) >> 1);
+    if ((long long)keys[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  *lb = lo;
+  unsigned e = lo;
+  if (lo < m && (long long)keys[lo] == v) {
+    e = lo + 1;                                     // unique build keys (the usual case) stop here
+    if (e < m && (long long)keys[e] == v) {
+      unsigned l2 = e + 1, h2 = m;
+      while (l2 < h2) {
+        const unsigned mid = l2 + ((h2 - l2) >> 1);
+        if ((long long)keys[mid] <= v) l2 = mid + 1; else h2 = mid;
+      }
+      e = l2;
+    }
+  }
+  *ub = e;
+}
+
+template <class B, class P>
+__global__ void __launch_bounds__(kJoinBlock) join_count_kernel(const B *__restrict__ bkeys, unsigned m, const P *__restrict__ pkeys, long long n,
+                                                                unsigned long long *__restrict__ tile_counts) {
+  __shared__ unsigned long long s_w[kJoinWarps];
+  const long long base = (long long)blockIdx.x * kJoinTile;
+  unsigned long long c = 0;
+#pragma unroll
+  for (int k = 0; k < kJoinRounds; ++k) {
+    const long long i = base + k * kJoinBlock + threadIdx.x;
+    if (i < n) {
+      unsigned lb, ub;
+      equal_range<B>(bkeys, m, (long long)pkeys[i], &lb, &ub);
+      c += ub - lb;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < kJoinWarps; ++w) t += s_w[w];
+    tile_counts[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of the tile counts, one block; *total = number of pairs
+__global__ void __launch_bounds__(1024) join_scan_kernel(const unsigned long long *__restrict__ counts, unsigned long long *__restrict__ offsets,
+                                                         long long ntiles, unsigned long long *__restrict__ total) {
+  __shared__ unsigned long long s_part[1024];
+  const long long per = (ntiles + 1023) / 1024;
+  const long long b = min((long long)threadIdx.x * per, ntiles), e = min(b + per, ntiles);
+  unsigned long long sum = 0;
+  for (long long i = b; i < e; ++i) sum += counts[i];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < 1024; ++i) { const unsigned long long t = s_part[i]; s_part[i] = run; run += t; }
+    *total = run;
+  }
+  __syncthreads();
+  unsigned long long run = s_part[threadIdx.x];
+  for (long long i = b; i < e; ++i) { offsets[i] = run; run += counts[i]; }
+}
+
+template <class B, class P>
+__global__ void __launch_bounds__(kJoinBlock) join_emit_kernel(const B *__restrict__ bkeys, const unsigned *__restrict__ brows, unsigned m,
+                                                               const P *__restrict__ pkeys, long long n,
+                                                               const unsigned long long *__restrict__ tile_offsets,
+                                                               long long *__restrict__ out_probe, long long *__restrict__ out_build) {
+  __shared__ unsigned long long s_w[kJoinWarps];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const long long base = (long long)blockIdx.x * kJoinTile;
+  unsigned long long run = tile_offsets[blockIdx.x];
+  for (int k = 0; k < kJoinRounds; ++k) {            // rows of one round are consecutive over the threads: output order = row order
+    const long long i = base + k * kJoinBlock + threadIdx.x;
+    unsigned lb = 0, ub = 0;
+    if (i < n) equal_range<B>(bkeys, m, (long long)pkeys[i], &lb, &ub);
+    const unsigned long long cnt = ub - lb;
+    unsigned long long incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (unsigned)o) incl += y;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned long long wpre = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kJoinWarps; ++w) {
+      const unsigned long long t = s_w[w];
+      if ((unsigned)w < warp) wpre += t;
+      total += t;
+    }
+    unsigned long long pos = run + wpre + incl - cnt;
+    for (unsigned q = lb; q < ub; ++q, ++pos) {
+      if (out_probe) out_probe[pos] = i;
+      if (out_build) out_build[pos] = (long long)brows[q];
+    }
+    run += total;
+    __syncthreads();
+  }
+}
+
+template <class T>
+__global__ void gather_rows_kernel(const T *__restrict__ src, const long long *__restrict__ rows, T *__restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[rows[i]];
+}
+
+static unsigned join_grid(Device *d, long long n) {
+  return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)d->num_sms * 16));
+}
+
+}  // namespace wdb
+
+using namespace wdb;
+
+struct wdb_join {
+  Device *dev = nullptr;
+  int key_dtype = WDB_INT32;
+  int64_t m = 0;
+  void *keys = nullptr;        // ascending signed keys (int or long long)
+  unsigned *rows = nullptr;    // build row of every sorted position
+};
+
+template <class B, class P>
+static int join_probe_typed(wdb_join *j, cudaStream_t s, const void *probe_keys, long long n, long long ntiles, int64_t *d_probe_rows,
+                            int64_t *d_build_rows, int64_t cap, int64_t *h_pairs) {
+  Scratch scratch;
+  WDB_CUDA(scratch.alloc(8 * (2 * (size_t)ntiles + 1), s));
+  unsigned long long *counts = scratch.as<unsigned long long>(), *offsets = counts + ntiles, *total = offsets + ntiles;
+  const B *bkeys = static_cast<const B *>(j->keys);
+  const P *pkeys = static_cast<const P *>(probe_keys);
+  const unsigned m = (unsigned)j->m;
+  join_count_kernel<B, P><<<(unsigned)ntiles, kJoinBlock, 0, s>>>(bkeys, m, pkeys, n, counts);
+  join_scan_kernel<<<1, 1024, 0, s>>>(counts, offsets, ntiles, total);
+  stats().launches += 2;
+  WDB_CUDA(cudaGetLastError());
+  unsigned long long pairs = 0;
+  WDB_CUDA(cudaMemcpyAsync(&pairs, total, 8, cudaMemcpyDeviceToHost, s));
+  WDB_CUDA(cudaStreamSynchronize(s));
+  if (h_pairs) *h_pairs = (int64_t)pairs;
+  if (!d_probe_rows && !d_build_rows) return 0;     // count only: the caller sizes its buffers from *h_pairs
+  if ((long long)pairs > cap) return fail("%lld joined rows exceed the output capacity %lld", (long long)pairs, (long long)cap);
+  if (pairs == 0) return 0;
+  join_emit_kernel<B, P><<<(unsigned)ntiles, kJoinBlock, 0, s>>>(bkeys, j->rows, m, pkeys, n, offsets, (long long *)d_probe_rows, (long long *)d_build_rows);
+  stats().launches++;
+  WDB_CUDA(cudaGetLastError());
+  WDB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" {
+
+int wdb_join_build(int device, void *stream, const wdb_col_t *build_key, wdb_join_t **out) {
+  Device *d;
+  if (get_device(device, &d)) return 1;
+  if (!build_key || !out) return fail("null argument");
+  if (build_key->dtype != WDB_INT32 && build_key->dtype != WDB_INT64)
+    return fail("JOIN needs integer key columns (%s is not one)", build_key->name ? build_key->name : "?");
+  const long long m = build_key->len;
+  if (m < 0) return fail("negative row count");
+  if (m >= (1ll << 32)) return fail("the build side of a JOIN is limited to 2^32 - 1 rows (%lld given)", m);
+  cudaStream_t s = (cudaStream_t)stream;
+  wdb_join *j = new wdb_join;
+  j->dev = d;
+  j->key_dtype = build_key->dtype;
+  j->m = m;
+  *out = j;
+  if (m == 0) return 0;
+  const size_t ksz = build_key->dtype == WDB_INT32 ? 4 : 8;
+  auto bail = [&](int rc) { wdb_join_destroy(j); *out = nullptr; return rc; };
+  if (cudaMalloc(&j->keys, ksz * (size_t)m) != cudaSuccess || cudaMalloc((void **)&j->rows, 4 * (size_t)m) != cudaSuccess) {
+    cudaGetLastError();
+    return bail(fail("CUDA error: out of memory (join index of %lld rows)", m));
+  }
+  Scratch tmp;
+  if (tmp.alloc((ksz + 4) * (size_t)m, s) != cudaSuccess) { cudaGetLastError(); return bail(fail("CUDA error: out of memory (join sort scratch)")); }
+  const unsigned g = join_grid(d, m);
+  int rc = 0;
+  if (build_key->dtype == WDB_INT32) {
+    unsigned *k = (unsigned *)j->keys, *kt = tmp.as<unsigned>(), *rt = kt + m;
+    join_encode_kernel<int, unsigned><<<g, 256, 0, s>>>((const int *)build_key->dptr, k, j->rows, m);
+    rc = radix_sort<unsigned>(d, s, k, kt, j->rows, rt, m, 32);
+    if (!rc) join_decode_kernel<int, unsigned><<<g, 256, 0, s>>>(k, m);
+  } else {
+    unsigned long long *k = (unsigned long long *)j->keys, *kt = tmp.as<unsigned long long>();
+    unsigned *rt = (unsigned *)(kt + m);
+    join_encode_kernel<long long, unsigned long long><<<g, 256, 0, s>>>((const long long *)build_key->dptr, k, j->rows, m);
+    rc = radix_sort<unsigned long long>(d, s, k, kt, j->rows, rt, m, 64);
+    if (!rc) join_decode_kernel<long long, unsigned long long><<<g, 256, 0, s>>>(k, m);
+  }
+  stats().launches += 2;
+  if (rc) return bail(1);
+  if (cudaGetLastError() != cudaSuccess) return bail(fail("CUDA error: join build launch failed"));
+  return 0;
+}
+
+int wdb_join_destroy(wdb_join_t *j) {
+  if (!j) return 0;
+  if (j->dev) cudaSetDevice(j->dev->id);
+  if (j->keys || j->rows) cudaDeviceSynchronize();
+  if (j->keys) cudaFree(j->keys);
+  if (j->rows) cudaFree(j->rows);
+  delete j;
+  return 0;
+}
+
+int wdb_join_info(const wdb_join_t *j, int64_t *build_rows, int *key_dtype) {
+  if (!j) return fail("null join index");
+  if (build_rows) *build_rows = j->m;
+  if (key_dtype) *key_dtype = j->key_dtype;
+  return 0;
+}
+
+int wdb_join_probe(wdb_join_t *j, void *stream, const wdb_col_t *probe_key, int64_t *d_probe_rows, int64_t *d_build_rows, int64_t cap,
+                   int64_t *h_pairs) {
+  if (!j || !probe_key) return fail("null argument");
+  if (probe_key->dtype != WDB_INT32 && probe_key->dtype != WDB_INT64)
+    return fail("JOIN needs integer key columns (%s is not one)", probe_key->name ? probe_key->name : "?");
+  Device *d = j->dev;
+  WDB_CUDA(cudaSetDevice(d->id));
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = probe_key->len;
+  if (n < 0) return fail("negative row count");
+  if (h_pairs) *h_pairs = 0;
+  if (n == 0 || j->m == 0) return 0;
+  const long long ntiles = (n + kJoinTile - 1) / kJoinTile;
+  if (ntiles > 0x7fffffffll) return fail("the probe side of a JOIN is limited to 2^41 rows");
+  const bool b32 = j->key_dtype == WDB_INT32, p32 = probe_key->dtype == WDB_INT32;
+  if (b32 && p32) return join_probe_typed<int, int>(j, s, probe_key->dptr, n, ntiles, d_probe_rows, d_build_rows, cap, h_pairs);
+  if (b32) return join_probe_typed<int, long long>(j, s, probe_key->dptr, n, ntiles, d_probe_rows, d_build_rows, cap, h_pairs);
+  if (p32) return join_probe_typed<long long, int>(j, s, probe_key->dptr, n, ntiles, d_probe_rows, d_build_rows, cap, h_pairs);
+  return join_probe_typed<long long, long long>(j, s, probe_key->dptr, n, ntiles, d_probe_rows, d_build_rows, cap, h_pairs);
+}
+
+int wdb_gather(int device, void *stream, const wdb_col_t *src, const int64_t *d_rows, int64_t count, void *d_dst) {
+  Device *d;
+  if (get_device(device, &d)) return 1;
+  if (count < 0) return fail("negative count");
+  if (count == 0) return 0;
+  if (!src || !d_dst) return fail("null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t esz = 0;
+  switch (src->dtype) {
+  case WDB_INT32: case WDB_FLOAT32: esz = 4; break;
+  case WDB_INT64: case WDB_FLOAT64: esz = 8; break;
+  default: return fail("column %s has a non-numeric type", src->name ? src->name : "?");
+  }
+  if (!d_rows) {                                    // identity row map
+    if (count > src->len) return fail("gather of %lld rows from a column of %lld", (long long)count, (long long)src->len);
+    WDB_CUDA(cudaMemcpyAsync(d_dst, src->dptr, esz * (size_t)count, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
+  const unsigned g = join_grid(d, count);
+  if (esz == 4) gather_rows_kernel<unsigned><<<g, 256, 0, s>>>((const unsigned *)src->dptr, (const long long *)d_rows, (unsigned *)d_dst, count);
+  else gather_rows_kernel<unsigned long long><<<g, 256, 0, s>>>((const unsigned long long *)src->dptr, (const long long *)d_rows, (unsigned long long *)d_dst, count);
+  stats().launches++;
+  WDB_CUDA(cudaGetLastError());
+  return 0;
+}
+}

@@ -301,6 +301,63 @@ def project_filter_pruned(table, expr, cond, preds, mode=wc.DENSE_ZERO, out=None
     return out, (cnt.value if sync else None), (live.value if sync else None)
 
 
+class JoinIndex:
+    """The build side of an inner equi-join (wdb_join_build): the (key, row) pairs of an int32 / int64
+    device column, sorted once, probed any number of times."""
+
+    def __init__(self, build_key, name="key"):
+        if not build_key.is_cuda or build_key.dim() != 1 or build_key.dtype not in (torch.int32, torch.int64):
+            raise wc.WarpcoreError("JoinIndex needs a 1-D int32/int64 CUDA tensor")
+        self.device = build_key.device.index or 0
+        self.rows = build_key.shape[0]
+        self.handle = C.c_void_p()
+        cols, _ = wc.make_cols([(name, _TORCH2DT[build_key.dtype], build_key.data_ptr(), self.rows)])
+        wc.check(wc.lib().wdb_join_build(self.device, _stream(self.device), cols, C.byref(self.handle)))
+
+    def count(self, probe_key):
+        """number of (probe row, build row) pairs with equal keys"""
+        cols, _ = wc.make_cols([("probe", _TORCH2DT[probe_key.dtype], probe_key.data_ptr(), probe_key.shape[0])])
+        n = C.c_int64(0)
+        wc.check(wc.lib().wdb_join_probe(self.handle, _stream(self.device), cols, None, None, 0, C.byref(n)))
+        return n.value
+
+    def probe(self, probe_key):
+        """(probe_rows, build_rows): int64 tensors, every pair with equal keys, ordered by probe row then build row"""
+        if not probe_key.is_cuda or probe_key.dim() != 1 or probe_key.dtype not in (torch.int32, torch.int64):
+            raise wc.WarpcoreError("probe needs a 1-D int32/int64 CUDA tensor")
+        pairs = self.count(probe_key)
+        pr = torch.empty(pairs, dtype=torch.int64, device=f"cuda:{self.device}")
+        br = torch.empty(pairs, dtype=torch.int64, device=f"cuda:{self.device}")
+        if pairs:
+            cols, _ = wc.make_cols([("probe", _TORCH2DT[probe_key.dtype], probe_key.data_ptr(), probe_key.shape[0])])
+            n = C.c_int64(0)
+            wc.check(wc.lib().wdb_join_probe(self.handle, _stream(self.device), cols, pr.data_ptr(), br.data_ptr(), pairs, C.byref(n)))
+            assert n.value == pairs
+        return pr, br
+
+    def close(self):
+        if self.handle:
+            wc.lib().wdb_join_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def gather(src, rows, out=None):
+    """out[i] = src[rows[i]] (wdb_gather); rows: int64 CUDA tensor, or None for a plain copy"""
+    dev = src.device.index or 0
+    count = src.shape[0] if rows is None else rows.shape[0]
+    if out is None:
+        out = torch.empty(count, dtype=src.dtype, device=src.device)
+    cols, _ = wc.make_cols([("src", _TORCH2DT[src.dtype], src.data_ptr(), src.shape[0])])
+    wc.check(wc.lib().wdb_gather(dev, _stream(dev), cols, None if rows is None else rows.data_ptr(), count, out.data_ptr()))
+    return out
+
+
 class Comm:
     """One GPU's membership in a group of GPUs (wdb_comm_*): the handle the sharded operators of the
     core (wdb_multi_*) take.  The cross-GPU merges run inside libwarpcore over NCCL/NVLink; Python only
