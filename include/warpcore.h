@@ -188,6 +188,8 @@ int wdb_topk_pruned(int device, void *stream, const wdb_col_t *cols, int ncols, 
  * build_key[j], ordered by i, then j (nested-loop order).  Keys are WDB_INT32 or WDB_INT64 columns
  * (the two sides may differ); the build side holds at most 2^32 - 1 rows.
  *   wdb_join_build   sorts (key, row) of the build column once; the index can be probed many times
+ *                    (from `stream`, or after it has drained).  A dense key range -- at most 8 key
+ *                    values per build row -- is also tabulated for direct addressing.
  *   wdb_join_probe   d_probe_rows == d_build_rows == NULL: count only (*h_pairs); otherwise the pairs
  *                    are written (cap = capacity of each array in pairs; more pairs than cap is an
  *                    error and nothing is written).  Synchronous: returns after the stream drained.
@@ -198,7 +200,8 @@ typedef struct wdb_join wdb_join_t;
 int wdb_join_build(int device, void *stream, const wdb_col_t *build_key, wdb_join_t **out);
 int wdb_join_probe(wdb_join_t *j, void *stream, const wdb_col_t *probe_key, int64_t *d_probe_rows, int64_t *d_build_rows, int64_t cap,
                    int64_t *h_pairs);
-int wdb_join_info(const wdb_join_t *j, int64_t *build_rows, int *key_dtype);
+/* direct_span: number of key values tabulated for direct addressing (0: probes binary-search) */
+int wdb_join_info(const wdb_join_t *j, int64_t *build_rows, int *key_dtype, int64_t *direct_span);
 int wdb_join_destroy(wdb_join_t *j);
 int wdb_gather(int device, void *stream, const wdb_col_t *src, const int64_t *d_rows, int64_t count, void *d_dst);
 

@@ -30,9 +30,16 @@ def check_pairs(probe, build):
     dp = torch.from_numpy(probe).cuda()
     assert idx.count(dp) == len(want_p)
     got_p, got_b = idx.probe(dp)
-    idx.close()
     assert np.array_equal(got_p.cpu().numpy(), want_p)
     assert np.array_equal(got_b.cpu().numpy(), want_b)
+    if idx.direct_span:                      # the same index probed by binary search instead of the key-range table
+        wc.set_option("join.direct", 0)
+        try:
+            alt_p, alt_b = idx.probe(dp)
+        finally:
+            wc.set_option("join.direct", None)
+        assert torch.equal(alt_p, got_p) and torch.equal(alt_b, got_b)
+    idx.close()
     return len(want_p)
 
 
@@ -76,6 +83,14 @@ def test_edges():
     h = C.c_void_p()
     with pytest.raises(wc.WarpcoreError, match="JOIN needs integer key columns"):
         wc.check(wc.lib().wdb_join_build(0, None, wc.make_cols([("f", wc.FLOAT32, f.data_ptr(), 4)])[0], C.byref(h)))
+
+
+def test_dense_key_ranges_are_tabulated():
+    ids = torch.randperm(100_000, dtype=torch.int32).cuda()
+    assert ops.JoinIndex(ids).direct_span == 100_000                       # ids of a dimension table
+    assert ops.JoinIndex(ids.long() * 1000).direct_span == 0               # sparse: 1000 key values per row
+    assert ops.JoinIndex(torch.tensor([5, 40_000], dtype=torch.int32).cuda()).direct_span == 39_996   # small tables: up to 2^16 values
+    assert ops.JoinIndex(torch.tensor([-(1 << 62), 1 << 62], dtype=torch.int64).cuda()).direct_span == 0
 
 
 def test_capacity_is_checked():

@@ -112,7 +112,7 @@ def lib():
     L.wdb_multi_topk_host.argtypes = [ci, C.POINTER(ci), PC, ci, cp, cp, cp, ci, i64, i64, i64, vp, P64]
     L.wdb_join_build.argtypes = [ci, vp, PC, C.POINTER(vp)]
     L.wdb_join_probe.argtypes = [vp, vp, PC, vp, vp, i64, P64]
-    L.wdb_join_info.argtypes = [vp, P64, C.POINTER(ci)]
+    L.wdb_join_info.argtypes = [vp, P64, C.POINTER(ci), P64]
     L.wdb_join_destroy.argtypes = [vp]
     L.wdb_gather.argtypes = [ci, vp, PC, vp, i64, vp]
     _lib = L

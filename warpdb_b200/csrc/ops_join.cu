@@ -9,7 +9,9 @@
 //
 // Sort-based, so the result order needs no post-pass and equal keys on either side are handled:
 //   build   (key, row) pairs of the build column, stable LSD radix sort by key (ops_sort.cu); equal
-//           keys keep their row order
+//           keys keep their row order.  When the key range is dense (ids of a dimension table) the lower
+//           bound of every key value of [min, max] is tabulated as well (4 B per value): a probe is then
+//           two adjacent loads instead of a binary search
 //   probe   two streaming passes over the probe column.  Pass 1 counts the matches of every 1 024-row
 //           tile (lower / upper bound in the sorted keys, which stay in L2 for dimension-sized build
 //           sides), one block scan turns the tile counts into offsets, pass 2 repeats the searches
@@ -74,8 +76,41 @@ __device__ __forceinline__ void equal_range(const B *__restrict__ keys, unsigned
   *ub = e;
 }
 
+// The probe's view of the index.  `first` (optional) is the direct-addressed form of the same sorted
+// keys: first[k - lo] = position of the first key >= k for k in [lo, lo + span], so the matches of v
+// are [first[v - lo], first[v - lo + 1]) -- two adjacent loads instead of ~log2(m) dependent ones.
+template <class B> struct JoinView {
+  const B *keys;
+  const unsigned *first;
+  long long lo, span;
+  unsigned m;
+};
+template <class B>
+__device__ __forceinline__ void join_lookup(const JoinView<B> &ix, long long v, unsigned *lb, unsigned *ub) {
+  if (ix.first) {
+    const unsigned long long k = (unsigned long long)v - (unsigned long long)ix.lo;   // v < lo wraps to a huge value
+    if (k < (unsigned long long)ix.span) { *lb = ix.first[k]; *ub = ix.first[k + 1]; }
+    else { *lb = 0; *ub = 0; }
+  } else {
+    equal_range<B>(ix.keys, ix.m, v, lb, ub);
+  }
+}
+// first[k] for k in [0, span]: one binary search per key value of the range, once per index
+template <class B>
+__global__ void join_first_kernel(const B *__restrict__ keys, unsigned m, long long lo, long long span, unsigned *__restrict__ first) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k <= span; k += (long long)gridDim.x * blockDim.x) {
+    const long long v = lo + k;
+    unsigned a = 0, b = m;
+    while (a < b) {
+      const unsigned mid = a + ((b - a) >> 1);
+      if ((long long)keys[mid] < v) a = mid + 1; else b = mid;
+    }
+    first[k] = a;
+  }
+}
+
 template <class B, class P>
-__global__ void __launch_bounds__(kJoinBlock) join_count_kernel(const B *__restrict__ bkeys, unsigned m, const P *__restrict__ pkeys, long long n,
+__global__ void __launch_bounds__(kJoinBlock) join_count_kernel(const JoinView<B> ix, const P *__restrict__ pkeys, long long n,
                                                                 unsigned long long *__restrict__ tile_counts) {
   __shared__ unsigned long long s_w[kJoinWarps];
   const long long base = (long long)blockIdx.x * kJoinTile;
@@ -85,7 +120,7 @@ __global__ void __launch_bounds__(kJoinBlock) join_count_kernel(const B *__restr
     const long long i = base + k * kJoinBlock + threadIdx.x;
     if (i < n) {
       unsigned lb, ub;
-      equal_range<B>(bkeys, m, (long long)pkeys[i], &lb, &ub);
+      join_lookup<B>(ix, (long long)pkeys[i], &lb, &ub);
       c += ub - lb;
     }
   }
@@ -121,7 +156,7 @@ __global__ void __launch_bounds__(1024) join_scan_kernel(const unsigned long lon
 }
 
 template <class B, class P>
-__global__ void __launch_bounds__(kJoinBlock) join_emit_kernel(const B *__restrict__ bkeys, const unsigned *__restrict__ brows, unsigned m,
+__global__ void __launch_bounds__(kJoinBlock) join_emit_kernel(const JoinView<B> ix, const unsigned *__restrict__ brows,
                                                                const P *__restrict__ pkeys, long long n,
                                                                const unsigned long long *__restrict__ tile_offsets,
                                                                long long *__restrict__ out_probe, long long *__restrict__ out_build) {
@@ -132,7 +167,7 @@ __global__ void __launch_bounds__(kJoinBlock) join_emit_kernel(const B *__restri
   for (int k = 0; k < kJoinRounds; ++k) {            // rows of one round are consecutive over the threads: output order = row order
     const long long i = base + k * kJoinBlock + threadIdx.x;
     unsigned lb = 0, ub = 0;
-    if (i < n) equal_range<B>(bkeys, m, (long long)pkeys[i], &lb, &ub);
+    if (i < n) join_lookup<B>(ix, (long long)pkeys[i], &lb, &ub);
     const unsigned long long cnt = ub - lb;
     unsigned long long incl = cnt;
 #pragma unroll
@@ -178,6 +213,8 @@ struct wdb_join {
   int64_t m = 0;
   void *keys = nullptr;        // ascending signed keys (int or long long)
   unsigned *rows = nullptr;    // build row of every sorted position
+  unsigned *first = nullptr;   // direct-addressed lower bounds over [lo, lo + span], when the key range is dense enough
+  long long lo = 0, span = 0;
 };
 
 template <class B, class P>
@@ -186,10 +223,9 @@ static int join_probe_typed(wdb_join *j, cudaStream_t s, const void *probe_keys,
   Scratch scratch;
   WDB_CUDA(scratch.alloc(8 * (2 * (size_t)ntiles + 1), s));
   unsigned long long *counts = scratch.as<unsigned long long>(), *offsets = counts + ntiles, *total = offsets + ntiles;
-  const B *bkeys = static_cast<const B *>(j->keys);
   const P *pkeys = static_cast<const P *>(probe_keys);
-  const unsigned m = (unsigned)j->m;
-  join_count_kernel<B, P><<<(unsigned)ntiles, kJoinBlock, 0, s>>>(bkeys, m, pkeys, n, counts);
+  const JoinView<B> ix{static_cast<const B *>(j->keys), opt("join.direct", 1) ? j->first : nullptr, j->lo, j->span, (unsigned)j->m};
+  join_count_kernel<B, P><<<(unsigned)ntiles, kJoinBlock, 0, s>>>(ix, pkeys, n, counts);
   join_scan_kernel<<<1, 1024, 0, s>>>(counts, offsets, ntiles, total);
   stats().launches += 2;
   WDB_CUDA(cudaGetLastError());
@@ -200,7 +236,7 @@ static int join_probe_typed(wdb_join *j, cudaStream_t s, const void *probe_keys,
   if (!d_probe_rows && !d_build_rows) return 0;     // count only: the caller sizes its buffers from *h_pairs
   if ((long long)pairs > cap) return fail("%lld joined rows exceed the output capacity %lld", (long long)pairs, (long long)cap);
   if (pairs == 0) return 0;
-  join_emit_kernel<B, P><<<(unsigned)ntiles, kJoinBlock, 0, s>>>(bkeys, j->rows, m, pkeys, n, offsets, (long long *)d_probe_rows, (long long *)d_build_rows);
+  join_emit_kernel<B, P><<<(unsigned)ntiles, kJoinBlock, 0, s>>>(ix, j->rows, pkeys, n, offsets, (long long *)d_probe_rows, (long long *)d_build_rows);
   stats().launches++;
   WDB_CUDA(cudaGetLastError());
   WDB_CUDA(cudaStreamSynchronize(s));
@@ -250,6 +286,34 @@ int wdb_join_build(int device, void *stream, const wdb_col_t *build_key, wdb_joi
   stats().launches += 2;
   if (rc) return bail(1);
   if (cudaGetLastError() != cudaSuccess) return bail(fail("CUDA error: join build launch failed"));
+  // Dense key range (ids of a dimension table): keep the lower bounds of every key value of [min, max]
+  // as well -- 4 B per value, at most join.direct_factor (8) values per build row
+  long long lo = 0, hi = -1;
+  if (build_key->dtype == WDB_INT32) {
+    int ends[2];
+    if (cudaMemcpyAsync(&ends[0], j->keys, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(&ends[1], (const int *)j->keys + (m - 1), 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+      return bail(fail("CUDA error: join build failed (%s)", cudaGetErrorString(cudaGetLastError())));
+    lo = ends[0]; hi = ends[1];
+  } else {
+    long long ends[2];
+    if (cudaMemcpyAsync(&ends[0], j->keys, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(&ends[1], (const long long *)j->keys + (m - 1), 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+      return bail(fail("CUDA error: join build failed (%s)", cudaGetErrorString(cudaGetLastError())));
+    lo = ends[0]; hi = ends[1];
+  }
+  const unsigned long long span = (unsigned long long)hi - (unsigned long long)lo + 1ull;   // 0 on the full int64 range
+  const unsigned long long limit = std::max<unsigned long long>((unsigned long long)opt("join.direct_factor", 8) * (unsigned long long)m, 1ull << 16);
+  if (opt("join.direct", 1) && span != 0 && span <= limit && span < (1ull << 30)) {
+    if (cudaMalloc((void **)&j->first, 4 * (size_t)(span + 1)) != cudaSuccess) { cudaGetLastError(); j->first = nullptr; return 0; }   // no room: binary search
+    j->lo = lo;
+    j->span = (long long)span;
+    const unsigned gf = join_grid(d, (long long)span + 1);
+    if (build_key->dtype == WDB_INT32) join_first_kernel<int><<<gf, 256, 0, s>>>((const int *)j->keys, (unsigned)m, lo, (long long)span, j->first);
+    else join_first_kernel<long long><<<gf, 256, 0, s>>>((const long long *)j->keys, (unsigned)m, lo, (long long)span, j->first);
+    stats().launches++;
+    if (cudaGetLastError() != cudaSuccess) return bail(fail("CUDA error: join build launch failed"));
+  }
   return 0;
 }
 
@@ -259,14 +323,16 @@ int wdb_join_destroy(wdb_join_t *j) {
   if (j->keys || j->rows) cudaDeviceSynchronize();
   if (j->keys) cudaFree(j->keys);
   if (j->rows) cudaFree(j->rows);
+  if (j->first) cudaFree(j->first);
   delete j;
   return 0;
 }
 
-int wdb_join_info(const wdb_join_t *j, int64_t *build_rows, int *key_dtype) {
+int wdb_join_info(const wdb_join_t *j, int64_t *build_rows, int *key_dtype, int64_t *direct_span) {
   if (!j) return fail("null join index");
   if (build_rows) *build_rows = j->m;
   if (key_dtype) *key_dtype = j->key_dtype;
+  if (direct_span) *direct_span = j->first ? j->span : 0;
   return 0;
 }
 

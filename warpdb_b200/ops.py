@@ -313,6 +313,9 @@ class JoinIndex:
         self.handle = C.c_void_p()
         cols, _ = wc.make_cols([(name, _TORCH2DT[build_key.dtype], build_key.data_ptr(), self.rows)])
         wc.check(wc.lib().wdb_join_build(self.device, _stream(self.device), cols, C.byref(self.handle)))
+        span = C.c_int64(0)
+        wc.check(wc.lib().wdb_join_info(self.handle, None, None, C.byref(span)))
+        self.direct_span = span.value          # > 0: probes index a table of the key range instead of searching
 
     def count(self, probe_key):
         """number of (probe row, build row) pairs with equal keys"""
