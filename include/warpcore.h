@@ -193,6 +193,9 @@ int wdb_topk_pruned(int device, void *stream, const wdb_col_t *cols, int ncols, 
  *   wdb_join_probe   d_probe_rows == d_build_rows == NULL: count only (*h_pairs); otherwise the pairs
  *                    are written (cap = capacity of each array in pairs; more pairs than cap is an
  *                    error and nothing is written).  Synchronous: returns after the stream drained.
+ *                    A count-only call leaves its per-tile counts in the index, and an emitting call
+ *                    on the same probe column (same pointer, length and type) that follows it reuses
+ *                    them instead of counting again -- do not modify the column between the two.
  *   wdb_gather       d_dst[i] = src[d_rows[i]] for i < count (4- and 8-byte column types; d_rows ==
  *                    NULL copies the first count rows): materialises the columns a joined query reads,
  *                    which the other operators then consume unchanged.  Rows are not range-checked. */

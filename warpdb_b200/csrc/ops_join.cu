@@ -21,6 +21,7 @@
 //           every other operator of the core (filter / project / GROUP BY / top-k) runs unchanged
 //           on the joined columns.
 #include <algorithm>
+#include <mutex>
 
 #include "core.hpp"
 
@@ -159,7 +160,8 @@ template <class B, class P>
 __global__ void __launch_bounds__(kJoinBlock) join_emit_kernel(const JoinView<B> ix, const unsigned *__restrict__ brows,
                                                                const P *__restrict__ pkeys, long long n,
                                                                const unsigned long long *__restrict__ tile_offsets,
-                                                               long long *__restrict__ out_probe, long long *__restrict__ out_build) {
+                                                               long long *__restrict__ out_probe, long long *__restrict__ out_build,
+                                                               unsigned long long cap) {
   __shared__ unsigned long long s_w[kJoinWarps];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const long long base = (long long)blockIdx.x * kJoinTile;
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(kJoinBlock) join_emit_kernel(const JoinView<B>
       total += t;
     }
     unsigned long long pos = run + wpre + incl - cnt;
-    for (unsigned q = lb; q < ub; ++q, ++pos) {
+    for (unsigned q = lb; q < ub && pos < cap; ++q, ++pos) {   // cap: never outside the caller's arrays, whatever the offsets say
       if (out_probe) out_probe[pos] = i;
       if (out_build) out_build[pos] = (long long)brows[q];
     }
@@ -215,28 +217,62 @@ struct wdb_join {
   unsigned *rows = nullptr;    // build row of every sorted position
   unsigned *first = nullptr;   // direct-addressed lower bounds over [lo, lo + span], when the key range is dense enough
   long long lo = 0, span = 0;
+  // pass 1 of the last count-only probe, kept for the emitting call that normally follows it
+  std::mutex mu;
+  struct { void *buf = nullptr; const void *probe = nullptr; long long n = 0; int dtype = 0; bool direct = false; unsigned long long pairs = 0; } counted;
 };
 
 template <class B, class P>
 static int join_probe_typed(wdb_join *j, cudaStream_t s, const void *probe_keys, long long n, long long ntiles, int64_t *d_probe_rows,
                             int64_t *d_build_rows, int64_t cap, int64_t *h_pairs) {
-  Scratch scratch;
-  WDB_CUDA(scratch.alloc(8 * (2 * (size_t)ntiles + 1), s));
-  unsigned long long *counts = scratch.as<unsigned long long>(), *offsets = counts + ntiles, *total = offsets + ntiles;
   const P *pkeys = static_cast<const P *>(probe_keys);
-  const JoinView<B> ix{static_cast<const B *>(j->keys), opt("join.direct", 1) ? j->first : nullptr, j->lo, j->span, (unsigned)j->m};
-  join_count_kernel<B, P><<<(unsigned)ntiles, kJoinBlock, 0, s>>>(ix, pkeys, n, counts);
-  join_scan_kernel<<<1, 1024, 0, s>>>(counts, offsets, ntiles, total);
-  stats().launches += 2;
-  WDB_CUDA(cudaGetLastError());
+  const bool direct = opt("join.direct", 1) != 0 && j->first != nullptr;
+  const JoinView<B> ix{static_cast<const B *>(j->keys), direct ? j->first : nullptr, j->lo, j->span, (unsigned)j->m};
+  const int pdtype = sizeof(P) == 4 ? WDB_INT32 : WDB_INT64;
+  const bool count_only = !d_probe_rows && !d_build_rows;
+  Scratch scratch;
   unsigned long long pairs = 0;
-  WDB_CUDA(cudaMemcpyAsync(&pairs, total, 8, cudaMemcpyDeviceToHost, s));
-  WDB_CUDA(cudaStreamSynchronize(s));
+  bool counted = false;
+  {  // a count of exactly this probe column, left by the previous call: its tile offsets are pass 1
+    std::lock_guard<std::mutex> lock(j->mu);
+    if (j->counted.buf) {
+      if (!count_only && j->counted.probe == probe_keys && j->counted.n == n && j->counted.dtype == pdtype && j->counted.direct == direct) {
+        scratch.p = j->counted.buf;
+        scratch.s = s;
+        pairs = j->counted.pairs;
+        counted = true;
+      } else {
+        cudaFreeAsync(j->counted.buf, s);
+      }
+      j->counted.buf = nullptr;
+    }
+  }
+  if (!counted) WDB_CUDA(scratch.alloc(8 * (2 * (size_t)ntiles + 1), s));
+  unsigned long long *counts = scratch.as<unsigned long long>(), *offsets = counts + ntiles, *total = offsets + ntiles;
+  if (!counted) {
+    join_count_kernel<B, P><<<(unsigned)ntiles, kJoinBlock, 0, s>>>(ix, pkeys, n, counts);
+    join_scan_kernel<<<1, 1024, 0, s>>>(counts, offsets, ntiles, total);
+    stats().launches += 2;
+    WDB_CUDA(cudaGetLastError());
+    WDB_CUDA(cudaMemcpyAsync(&pairs, total, 8, cudaMemcpyDeviceToHost, s));
+    WDB_CUDA(cudaStreamSynchronize(s));
+  }
   if (h_pairs) *h_pairs = (int64_t)pairs;
-  if (!d_probe_rows && !d_build_rows) return 0;     // count only: the caller sizes its buffers from *h_pairs
+  if (count_only) {                                   // the caller sizes its arrays from *h_pairs and calls again
+    std::lock_guard<std::mutex> lock(j->mu);
+    j->counted.buf = scratch.p;
+    scratch.p = nullptr;
+    j->counted.probe = probe_keys;
+    j->counted.n = n;
+    j->counted.dtype = pdtype;
+    j->counted.direct = direct;
+    j->counted.pairs = pairs;
+    return 0;
+  }
   if ((long long)pairs > cap) return fail("%lld joined rows exceed the output capacity %lld", (long long)pairs, (long long)cap);
   if (pairs == 0) return 0;
-  join_emit_kernel<B, P><<<(unsigned)ntiles, kJoinBlock, 0, s>>>(ix, j->rows, pkeys, n, offsets, (long long *)d_probe_rows, (long long *)d_build_rows);
+  join_emit_kernel<B, P><<<(unsigned)ntiles, kJoinBlock, 0, s>>>(ix, j->rows, pkeys, n, offsets, (long long *)d_probe_rows, (long long *)d_build_rows,
+                                                                 (unsigned long long)cap);
   stats().launches++;
   WDB_CUDA(cudaGetLastError());
   WDB_CUDA(cudaStreamSynchronize(s));
@@ -320,10 +356,11 @@ int wdb_join_build(int device, void *stream, const wdb_col_t *build_key, wdb_joi
 int wdb_join_destroy(wdb_join_t *j) {
   if (!j) return 0;
   if (j->dev) cudaSetDevice(j->dev->id);
-  if (j->keys || j->rows) cudaDeviceSynchronize();
+  if (j->keys || j->rows || j->counted.buf) cudaDeviceSynchronize();
   if (j->keys) cudaFree(j->keys);
   if (j->rows) cudaFree(j->rows);
   if (j->first) cudaFree(j->first);
+  if (j->counted.buf) cudaFree(j->counted.buf);
   delete j;
   return 0;
 }
