@@ -50,7 +50,7 @@ def main():
         print(json.dumps(rec), flush=True)
 
     wc.check(wc.lib().wdb_init(0))
-    for m in (1 << 20, 1 << 24):
+    for m in ([int(float(a)) for a in sys.argv[2:]] or [1 << 20, 1 << 24]):
         ids = torch.randperm(m, dtype=torch.int32, device="cuda")
         rate = torch.rand(m, device="cuda")
         probe = ops.synth_i32(n, 0xC0FFEE + 7, 0, m + m // 10)

@@ -9,9 +9,9 @@
 //
 // Sort-based, so the result order needs no post-pass and equal keys on either side are handled:
 //   build   (key, row) pairs of the build column, stable LSD radix sort by key (ops_sort.cu); equal
-//           keys keep their row order.  When the key range is dense (ids of a dimension table) the lower
-//           bound of every key value of [min, max] is tabulated as well (4 B per value): a probe is then
-//           two adjacent loads instead of a binary search
+//           keys keep their row order.  When the key range is dense (ids of a dimension table) every key
+//           value of [min, max] gets an 8-byte entry {matches, build row or first sorted position} as
+//           well: a probe is then one load instead of a binary search plus the row lookup
 //   probe   two streaming passes over the probe column.  Pass 1 counts the matches of every 1 024-row
 //           tile (lower / upper bound in the sorted keys, which stay in L2 for dimension-sized build
 //           sides), one block scan turns the tile counts into offsets, pass 2 repeats the searches
@@ -77,24 +77,36 @@ __device__ __forceinline__ void equal_range(const B *__restrict__ keys, unsigned
   *ub = e;
 }
 
-// The probe's view of the index.  `first` (optional) is the direct-addressed form of the same sorted
-// keys: first[k - lo] = position of the first key >= k for k in [lo, lo + span], so the matches of v
-// are [first[v - lo], first[v - lo + 1]) -- two adjacent loads instead of ~log2(m) dependent ones.
+// The probe's view of the index.  `tab` (optional) is the direct-addressed form of the same sorted
+// keys, one 8-byte entry per key value of [lo, lo + span): {matches, the build row itself when there
+// is exactly one match (distinct ids: the usual case), else the position of the first match in the
+// sorted order}.  A probe is then ONE load instead of ~log2(m) dependent ones plus the row lookup.
 template <class B> struct JoinView {
   const B *keys;
-  const unsigned *first;
+  const uint2 *tab;
   long long lo, span;
   unsigned m;
 };
+// number of matches of v; *ref = the build row (*is_row) or the sorted position of the first match
 template <class B>
-__device__ __forceinline__ void join_lookup(const JoinView<B> &ix, long long v, unsigned *lb, unsigned *ub) {
-  if (ix.first) {
+__device__ __forceinline__ unsigned join_lookup(const JoinView<B> &ix, long long v, unsigned *ref, bool *is_row) {
+  if (ix.tab) {
     const unsigned long long k = (unsigned long long)v - (unsigned long long)ix.lo;   // v < lo wraps to a huge value
-    if (k < (unsigned long long)ix.span) { *lb = ix.first[k]; *ub = ix.first[k + 1]; }
-    else { *lb = 0; *ub = 0; }
-  } else {
-    equal_range<B>(ix.keys, ix.m, v, lb, ub);
+    if (k < (unsigned long long)ix.span) {
+      const uint2 e = ix.tab[k];
+      *ref = e.y;
+      *is_row = e.x == 1u;
+      return e.x;
+    }
+    *ref = 0;
+    *is_row = false;
+    return 0;
   }
+  unsigned lb, ub;
+  equal_range<B>(ix.keys, ix.m, v, &lb, &ub);
+  *ref = lb;
+  *is_row = false;
+  return ub - lb;
 }
 // first[k] for k in [0, span]: one binary search per key value of the range, once per index
 template <class B>
@@ -110,6 +122,13 @@ __global__ void join_first_kernel(const B *__restrict__ keys, unsigned m, long l
   }
 }
 
+__global__ void join_tab_kernel(const unsigned *__restrict__ first, const unsigned *__restrict__ rows, long long span, uint2 *__restrict__ tab) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < span; k += (long long)gridDim.x * blockDim.x) {
+    const unsigned lb = first[k], cnt = first[k + 1] - lb;
+    tab[k] = make_uint2(cnt, cnt == 1u ? rows[lb] : lb);
+  }
+}
+
 template <class B, class P>
 __global__ void __launch_bounds__(kJoinBlock) join_count_kernel(const JoinView<B> ix, const P *__restrict__ pkeys, long long n,
                                                                 unsigned long long *__restrict__ tile_counts) {
@@ -120,9 +139,9 @@ __global__ void __launch_bounds__(kJoinBlock) join_count_kernel(const JoinView<B
   for (int k = 0; k < kJoinRounds; ++k) {
     const long long i = base + k * kJoinBlock + threadIdx.x;
     if (i < n) {
-      unsigned lb, ub;
-      join_lookup<B>(ix, (long long)pkeys[i], &lb, &ub);
-      c += ub - lb;
+      unsigned ref;
+      bool is_row;
+      c += join_lookup<B>(ix, (long long)pkeys[i], &ref, &is_row);
     }
   }
 #pragma unroll
@@ -166,11 +185,23 @@ __global__ void __launch_bounds__(kJoinBlock) join_emit_kernel(const JoinView<B>
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const long long base = (long long)blockIdx.x * kJoinTile;
   unsigned long long run = tile_offsets[blockIdx.x];
+  // all lookups of the tile first (independent loads in flight), then one block scan per round
+  unsigned refs[kJoinRounds], cs[kJoinRounds];
+  bool is_rows[kJoinRounds];
+#pragma unroll
+  for (int k = 0; k < kJoinRounds; ++k) {
+    const long long i = base + k * kJoinBlock + threadIdx.x;
+    refs[k] = 0;
+    cs[k] = 0;
+    is_rows[k] = false;
+    if (i < n) cs[k] = join_lookup<B>(ix, (long long)pkeys[i], &refs[k], &is_rows[k]);
+  }
+#pragma unroll
   for (int k = 0; k < kJoinRounds; ++k) {            // rows of one round are consecutive over the threads: output order = row order
     const long long i = base + k * kJoinBlock + threadIdx.x;
-    unsigned lb = 0, ub = 0;
-    if (i < n) join_lookup<B>(ix, (long long)pkeys[i], &lb, &ub);
-    const unsigned long long cnt = ub - lb;
+    const unsigned ref = refs[k], c = cs[k];
+    const bool is_row = is_rows[k];
+    const unsigned long long cnt = c;
     unsigned long long incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -187,9 +218,16 @@ __global__ void __launch_bounds__(kJoinBlock) join_emit_kernel(const JoinView<B>
       total += t;
     }
     unsigned long long pos = run + wpre + incl - cnt;
-    for (unsigned q = lb; q < ub && pos < cap; ++q, ++pos) {   // cap: never outside the caller's arrays, whatever the offsets say
-      if (out_probe) out_probe[pos] = i;
-      if (out_build) out_build[pos] = (long long)brows[q];
+    if (is_row) {                                      // cap: never outside the caller's arrays, whatever the offsets say
+      if (pos < cap) {
+        if (out_probe) out_probe[pos] = i;
+        if (out_build) out_build[pos] = (long long)ref;
+      }
+    } else {
+      for (unsigned q = 0; q < c && pos < cap; ++q, ++pos) {
+        if (out_probe) out_probe[pos] = i;
+        if (out_build) out_build[pos] = (long long)brows[ref + q];
+      }
     }
     run += total;
     __syncthreads();
@@ -215,7 +253,7 @@ struct wdb_join {
   int64_t m = 0;
   void *keys = nullptr;        // ascending signed keys (int or long long)
   unsigned *rows = nullptr;    // build row of every sorted position
-  unsigned *first = nullptr;   // direct-addressed lower bounds over [lo, lo + span], when the key range is dense enough
+  uint2 *tab = nullptr;        // direct-addressed {matches, row or first position} over [lo, lo + span), when the key range is dense enough
   long long lo = 0, span = 0;
   // pass 1 of the last count-only probe, kept for the emitting call that normally follows it
   std::mutex mu;
@@ -226,8 +264,8 @@ template <class B, class P>
 static int join_probe_typed(wdb_join *j, cudaStream_t s, const void *probe_keys, long long n, long long ntiles, int64_t *d_probe_rows,
                             int64_t *d_build_rows, int64_t cap, int64_t *h_pairs) {
   const P *pkeys = static_cast<const P *>(probe_keys);
-  const bool direct = opt("join.direct", 1) != 0 && j->first != nullptr;
-  const JoinView<B> ix{static_cast<const B *>(j->keys), direct ? j->first : nullptr, j->lo, j->span, (unsigned)j->m};
+  const bool direct = opt("join.direct", 1) != 0 && j->tab != nullptr;
+  const JoinView<B> ix{static_cast<const B *>(j->keys), direct ? j->tab : nullptr, j->lo, j->span, (unsigned)j->m};
   const int pdtype = sizeof(P) == 4 ? WDB_INT32 : WDB_INT64;
   const bool count_only = !d_probe_rows && !d_build_rows;
   Scratch scratch;
@@ -322,8 +360,8 @@ int wdb_join_build(int device, void *stream, const wdb_col_t *build_key, wdb_joi
   stats().launches += 2;
   if (rc) return bail(1);
   if (cudaGetLastError() != cudaSuccess) return bail(fail("CUDA error: join build launch failed"));
-  // Dense key range (ids of a dimension table): keep the lower bounds of every key value of [min, max]
-  // as well -- 4 B per value, at most join.direct_factor (8) values per build row
+  // Dense key range (ids of a dimension table): tabulate every key value of [min, max] as well --
+  // 8 B per value, at most join.direct_factor (8) values per build row
   long long lo = 0, hi = -1;
   if (build_key->dtype == WDB_INT32) {
     int ends[2];
@@ -340,14 +378,17 @@ int wdb_join_build(int device, void *stream, const wdb_col_t *build_key, wdb_joi
   }
   const unsigned long long span = (unsigned long long)hi - (unsigned long long)lo + 1ull;   // 0 on the full int64 range
   const unsigned long long limit = std::max<unsigned long long>((unsigned long long)opt("join.direct_factor", 8) * (unsigned long long)m, 1ull << 16);
-  if (opt("join.direct", 1) && span != 0 && span <= limit && span < (1ull << 30)) {
-    if (cudaMalloc((void **)&j->first, 4 * (size_t)(span + 1)) != cudaSuccess) { cudaGetLastError(); j->first = nullptr; return 0; }   // no room: binary search
+  if (opt("join.direct", 1) && span != 0 && span <= limit && span < (1ull << 28)) {
+    Scratch first;
+    if (first.alloc(4 * (size_t)(span + 1), s) != cudaSuccess) { cudaGetLastError(); return 0; }                              // no room: probes binary-search
+    if (cudaMalloc((void **)&j->tab, 8 * (size_t)span) != cudaSuccess) { cudaGetLastError(); j->tab = nullptr; return 0; }
     j->lo = lo;
     j->span = (long long)span;
     const unsigned gf = join_grid(d, (long long)span + 1);
-    if (build_key->dtype == WDB_INT32) join_first_kernel<int><<<gf, 256, 0, s>>>((const int *)j->keys, (unsigned)m, lo, (long long)span, j->first);
-    else join_first_kernel<long long><<<gf, 256, 0, s>>>((const long long *)j->keys, (unsigned)m, lo, (long long)span, j->first);
-    stats().launches++;
+    if (build_key->dtype == WDB_INT32) join_first_kernel<int><<<gf, 256, 0, s>>>((const int *)j->keys, (unsigned)m, lo, (long long)span, first.as<unsigned>());
+    else join_first_kernel<long long><<<gf, 256, 0, s>>>((const long long *)j->keys, (unsigned)m, lo, (long long)span, first.as<unsigned>());
+    join_tab_kernel<<<gf, 256, 0, s>>>(first.as<unsigned>(), j->rows, (long long)span, j->tab);
+    stats().launches += 2;
     if (cudaGetLastError() != cudaSuccess) return bail(fail("CUDA error: join build launch failed"));
   }
   return 0;
@@ -359,7 +400,7 @@ int wdb_join_destroy(wdb_join_t *j) {
   if (j->keys || j->rows || j->counted.buf) cudaDeviceSynchronize();
   if (j->keys) cudaFree(j->keys);
   if (j->rows) cudaFree(j->rows);
-  if (j->first) cudaFree(j->first);
+  if (j->tab) cudaFree(j->tab);
   if (j->counted.buf) cudaFree(j->counted.buf);
   delete j;
   return 0;
@@ -369,7 +410,7 @@ int wdb_join_info(const wdb_join_t *j, int64_t *build_rows, int *key_dtype, int6
   if (!j) return fail("null join index");
   if (build_rows) *build_rows = j->m;
   if (key_dtype) *key_dtype = j->key_dtype;
-  if (direct_span) *direct_span = j->first ? j->span : 0;
+  if (direct_span) *direct_span = j->tab ? j->span : 0;
   return 0;
 }
 
