@@ -744,6 +744,7 @@ std::vector<float> WarpDB::query_sql_multi_gpu(const std::string &sql) {
     for (const auto &k : ast.group_by->keys) validate_ast(k.get(), cols);
   if (ast.order_by) validate_ast(ast.order_by->expr.get(), cols);
   if (ast.select_list.empty()) throw std::runtime_error("Empty select list");
+  if (!ast.joins.empty()) throw std::runtime_error("JOIN is not supported on the multi-GPU path (query_sql runs it on one GPU)");
   if (ast.having || ast.distinct) throw std::runtime_error("HAVING and DISTINCT are not supported on the multi-GPU path");
   refresh_udf_source();
   const std::string cond = ast.where ? (*ast.where)->to_cuda_expr() : std::string();
