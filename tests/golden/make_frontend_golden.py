@@ -70,6 +70,20 @@ QUERIES = [
     "SELECT f(price, quantity), price FROM t", "SELECT (price + 1) * 2, quantity FROM t WHERE quantity = 2",
     "SELECT price FROM t WHERE price > 1 GROUP BY quantity HAVING 2 > 1 ORDER BY quantity DESC LIMIT 4 OFFSET 1",
     "SELECT price\nFROM t\nWHERE price > 1\nLIMIT", "SELECT price FROM t WHERE price # 1", "",
+    # JOIN statements the product executes (tests/test_gpu_join.py); the reference parses them and stops there
+    "SELECT price * rate FROM sales JOIN items ON sales.item = items.id",
+    "SELECT sales.price * items.rate FROM sales JOIN items ON item = id WHERE items.rate > 0.5 AND sales.quantity < 5",
+    "SELECT price FROM sales JOIN items ON items.id == sales.item WHERE cat == 3",
+    "SELECT SUM(price * rate) FROM sales JOIN items ON sales.item = items.id GROUP BY cat",
+    "SELECT AVG(price) FROM sales JOIN items ON sales.item = items.id WHERE quantity > 2 GROUP BY cat ORDER BY cat DESC",
+    "SELECT COUNT(price) FROM sales JOIN items ON sales.item = items.id GROUP BY cat, quantity",
+    "SELECT price * rate FROM sales JOIN items ON sales.item = items.id ORDER BY price * rate DESC LIMIT 7",
+    "SELECT DISTINCT cat FROM sales JOIN items ON sales.item = items.id ORDER BY cat ASC",
+    "SELECT price FROM sales JOIN items ON sales.item = items.id WHERE price > 99 LIMIT 5 OFFSET 2",
+    "SELECT price * rate * boost FROM sales JOIN items ON sales.item = items.id JOIN cats ON items.cat = cats.cid WHERE quantity > 1",
+    "SELECT sales.price - other.price FROM sales JOIN other ON sales.item = other.item WHERE sales.quantity > other.quantity",
+    "SELECT price FROM sales JOIN items ON sales.item > items.id", "SELECT price FROM sales JOIN ON a = b",
+    "SELECT price FROM sales JOIN items ON sales.item = items.id JOIN", "SELECT price FROM sales JOIN items sales.item = items.id",
 ]
 
 def esc(s):
