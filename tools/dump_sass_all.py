@@ -59,3 +59,24 @@ for name, kind, a, b, cond, mode, opts, fn in JOBS:
         f.write("// mnemonic histogram: " + ", ".join(f"{k} x{v}" for k, v in sorted(hist.items())) + "\n")
         f.write("\n".join(lines) + "\n")
     print(name, len(lines), "instructions")
+
+# ---- kernels compiled ahead of time into libwarpcore.so (nvcc): the join's probe kernels ------------
+LIB = os.path.join(ROOT, "warpdb_b200", "libwarpcore.so")
+STATIC = [("join_count_kernel_i32_i32", "join_count_kernelIiiEE"), ("join_emit_kernel_i32_i32", "join_emit_kernelIiiEE")]
+sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
+res = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True, check=True).stdout.splitlines()
+for name, tag in STATIC:
+    chunk = [c for c in sass.split("Function : ")[1:] if tag in c.split("\n", 1)[0]][0]
+    mangled = chunk.split("\n", 1)[0].strip()
+    lines = []
+    for ln in chunk.splitlines():
+        m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
+        if m:
+            lines.append(f"/*{m.group(1)}*/ {m.group(2).strip()} ;")
+    hist = collections.Counter(m.group(0) for ln in lines for m in [INTEREST.search(ln)] if m)
+    usage = [res[i + 1].strip() for i, l in enumerate(res) if mangled in l and i + 1 < len(res)]
+    with open(os.path.join(OUT, name + ".sass"), "w") as f:
+        f.write(f"// {mangled}  (warpdb_b200/csrc/ops_join.cu, nvcc 12.9 -gencode arch=compute_100a,code=sm_100a, cuobjdump -sass)\n")
+        f.write("// " + " | ".join(usage) + "\n")
+        f.write("// mnemonic histogram: " + ", ".join(f"{k} x{v}" for k, v in sorted(hist.items())) + "\n")
+        f.write("\n".join(lines) + "\n")
